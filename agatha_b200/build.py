@@ -1,0 +1,80 @@
+"""Build libagatha_b200.so (C ABI, include/agatha_b200.h) in-tree with nvcc for sm_100a.
+
+    python -m agatha_b200.build [--force]
+
+The .so is git-ignored but travels to the GPU box with the repository snapshot.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIBDIR = os.path.join(PKG, "lib")
+LIB = os.path.join(LIBDIR, "libagatha_b200.so")
+STAMP = os.path.join(LIBDIR, "libagatha_b200.stamp")
+
+CUDA_SOURCES = ["engine.cu", "stream.cu"]
+CXX_SOURCES = ["host_utils.cpp", "fasta.cpp", "synth.cpp", "job.cpp", "gasal_compat.cpp"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fopenmp,-Wall", "--default-stream", "per-thread"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in CUDA_SOURCES + CXX_SOURCES if os.path.exists(os.path.join(CSRC, f))]
+
+
+def _digest():
+    h = hashlib.sha256()
+    files = sorted([os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h"))])
+    files += [os.path.join(ROOT, "include", f) for f in sorted(os.listdir(os.path.join(ROOT, "include")))]
+    for f in files:
+        h.update(f.encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return LIB
+    objs = []
+    procs = []
+    for src in _sources():
+        obj = os.path.join(LIBDIR, os.path.basename(src) + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-c", src, "-o", obj]
+        if src.endswith(".cpp"):
+            cmd = [_nvcc()] + NVCC_FLAGS + ["-x", "cu", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (src, out))
+        if verbose and out.strip():
+            print(out)
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lgomp", "-lpthread"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    with open(STAMP, "w") as f:
+        f.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

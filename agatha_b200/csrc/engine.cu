@@ -1,0 +1,177 @@
+// Device-level entry points of the C ABI (include/agatha_b200.h): packing and the extension kernel launch.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "extend_kernel.cuh"
+#include "pack_kernel.cuh"
+#include "engine_internal.h"
+
+namespace agatha {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_error(cudaError_t e, const char* what)
+{
+    return set_error(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? AGATHA_ENODEV : AGATHA_ECUDA,
+                     "%s: %s", what, cudaGetErrorString(e));
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// cells per lane for a band width: one warp covers global cell indices g in [0, 32*C), the band needs g <= W
+static int cells_per_lane(int W)
+{
+    if (W < 32 * 8) return 8;
+    if (W < 32 * 16) return 16;
+    if (W < 32 * 24) return 24;
+    if (W < 32 * 32) return 32;
+    return 0;
+}
+
+template <int C, bool WODD, int JWS>
+static int launch_variant(const JobArrays& ja, const KernelParams& kp, cudaStream_t st)
+{
+    static int blocks_per_sm = 0;
+    static int sms = 0;
+    if (!blocks_per_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int b = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, extend_kernel<C, WODD, JWS>, 128, 0);
+        blocks_per_sm = b > 0 ? b : 1;
+    }
+    // persistent warps: never more warps than jobs, otherwise fill every SM
+    long long want = ((long long)ja.n + 3) / 4;
+    long long grid = (long long)sms * blocks_per_sm;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    extend_kernel<C, WODD, JWS><<<(unsigned)grid, 128, 0, st>>>(ja, kp);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_error(e, "extend_kernel launch");
+    return AGATHA_OK;
+}
+
+template <int C>
+static int launch_c(const JobArrays& ja, const KernelParams& kp, cudaStream_t st)
+{
+    const bool wodd = kp.W & 1;
+    if (wodd) {
+        if (kp.JW == 7) return launch_variant<C, true, 7>(ja, kp, st);       // every W == 7 (mod 8) with C == 8; W=751 with C == 24
+        return launch_variant<C, true, -1>(ja, kp, st);
+    }
+    return launch_variant<C, false, -1>(ja, kp, st);
+}
+
+int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
+{
+    if (!p) return set_error(AGATHA_EINVAL, "params is NULL");
+    if (p->band_width < 0) return set_error(AGATHA_EINVAL, "band_width < 0");
+    if (p->slice_width < 1) return set_error(AGATHA_EINVAL, "slice_width < 1");
+    const int C = cells_per_lane(p->band_width);
+    if (!C) return set_error(AGATHA_EUNSUPPORTED, "band_width %d > %d not supported by this build", p->band_width, agatha_max_band_width());
+    kp->match = p->match; kp->mismatch = p->mismatch;
+    kp->goe = p->gap_open + p->gap_extend;          // gasal_align.cu:301
+    kp->ge = p->gap_extend;
+    kp->sw = p->slice_width; kp->Z = p->z_threshold; kp->W = p->band_width;
+    kp->LW = p->band_width / C; kp->JW = p->band_width % C;
+    // PRMT table over x = query code ^ target code: 0 match, 1..3 mismatch, 4..7 N vs base (-N_PENALTY = -1);
+    // x >= 8 selects the sign of entry x&7 replicated: 0xff == -1 for every negative entry (extend_kernel.cuh)
+    const unsigned m = (unsigned)p->match & 0xffu, x = (unsigned)(-p->mismatch) & 0xffu;
+    kp->tab_lo = m | (x << 8) | (x << 16) | (x << 24);
+    kp->tab_hi = 0xffffffffu;
+    return AGATHA_OK;
+}
+
+bool fast_table_ok(const agatha_params_t* p)
+{
+    return p->match >= -128 && p->match <= 127 && p->mismatch >= 1 && p->mismatch <= 128;
+}
+
+}  // namespace agatha
+
+using namespace agatha;
+
+extern "C" {
+
+const char* agatha_last_error(void) { return g_err; }
+
+int agatha_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int agatha_max_band_width(void) { return 32 * 32 - 1; }
+
+uint64_t agatha_launch_count(void) { return g_launches.load(); }
+
+int agatha_pack_device(const uint8_t* d_query_bases, uint64_t query_bytes, const uint8_t* d_target_bases, uint64_t target_bytes,
+                       uint32_t* d_query_packed, uint32_t* d_target_packed, void* stream)
+{
+    if ((query_bytes & 7) || (target_bytes & 7)) return set_error(AGATHA_EINVAL, "batch bytes must be multiples of 8");
+    if (query_bytes + target_bytes == 0) return AGATHA_OK;
+    if (agatha_device_count() == 0) return set_error(AGATHA_ENODEV, "no CUDA device");
+    const uint64_t words = (query_bytes + target_bytes) / 8;
+    uint64_t blocks = (words + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint2*)d_query_bases, query_bytes / 8,
+                                                                     (const uint2*)d_target_bases, target_bytes / 8,
+                                                                     d_query_packed, d_target_packed);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_error(e, "pack_kernel launch");
+    return AGATHA_OK;
+}
+
+int agatha_extend_device(const uint32_t* d_query_packed, const uint32_t* d_target_packed,
+                         const uint32_t* d_query_offsets, const uint32_t* d_target_offsets,
+                         const uint32_t* d_query_lens, const uint32_t* d_target_lens,
+                         const uint32_t* d_order, uint32_t n_alns, const agatha_params_t* params,
+                         int32_t* d_score, int32_t* d_query_end, int32_t* d_target_end,
+                         int32_t* d_stop, int32_t* d_dstop, void* d_workspace, void* stream)
+{
+    if (n_alns == 0) return set_error(AGATHA_EINVAL, "n_alns == 0");
+    if (!d_query_packed || !d_target_packed || !d_query_offsets || !d_target_offsets || !d_query_lens || !d_target_lens ||
+        !d_score || !d_query_end || !d_target_end || !d_workspace)
+        return set_error(AGATHA_EINVAL, "NULL device pointer");
+    KernelParams kp;
+    int rc = make_kernel_params(params, &kp);
+    if (rc) return rc;
+    if (!fast_table_ok(params)) return set_error(AGATHA_EUNSUPPORTED, "match/mismatch outside the byte lookup table range");
+    if (agatha_device_count() == 0) return set_error(AGATHA_ENODEV, "no CUDA device");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_workspace, 0, AGATHA_WORKSPACE_BYTES, st);
+    if (e != cudaSuccess) return cuda_error(e, "workspace memset");
+    JobArrays ja;
+    ja.qpk = d_query_packed; ja.tpk = d_target_packed;
+    ja.qoff_w = d_query_offsets; ja.toff_w = d_target_offsets;
+    ja.qlen = d_query_lens; ja.tlen = d_target_lens;
+    ja.order = d_order;
+    ja.score = d_score; ja.qend = d_query_end; ja.tend = d_target_end; ja.stop = d_stop; ja.dstop = d_dstop;
+    ja.counter = (unsigned*)d_workspace;
+    ja.n = (int)n_alns;
+    switch (cells_per_lane(kp.W)) {
+        case 8: return launch_c<8>(ja, kp, st);
+        case 16: return launch_c<16>(ja, kp, st);
+        case 24: return launch_c<24>(ja, kp, st);
+        case 32: return launch_c<32>(ja, kp, st);
+    }
+    return set_error(AGATHA_EUNSUPPORTED, "no kernel for band_width %d", kp.W);
+}
+
+}  // extern "C"

@@ -1,0 +1,450 @@
+// Banded affine-gap extension with Z-drop for sm_100a: the hot path of this repository.
+//
+// Replaces the reference's agatha_kernel (AGAThA/src/kernels/agatha_kernel.h:49-431) + agatha_sort (:434-458);
+// same results (score, query end, target end), different algorithm layout. Parity spec: SURVEY.md Appendix A,
+// restated and pinned in oracle/agatha_oracle.c.
+//
+// Formulation: cells are addressed by anti-diagonal d = q + r and diagonal offset k = r - q.
+// In (d,k) space the band |r-q| <= W is a FIXED stripe, so a lane owns a fixed, contiguous k-range for the whole
+// alignment and its H/E/F state never leaves registers. One group of NW warps handles one alignment:
+//   global lane gl = warp_in_group*32 + lane owns k = -W + 2*(C*gl + j) + u,  j in [0,C), u in {0,1}
+// and step d updates the C cells of parity u = (d+W)&1 of every lane (they are mutually independent). A cell reads
+//   E from (d-1,k-1), F from (d-1,k+1), H from (d-2,k); only the first/last cell of a lane needs a neighbour lane
+// (one warp shuffle per step). The per-anti-diagonal maximum needed by the Z-drop test is a lane-local max of
+// (H*32+j) keys, one warp REDUX per step and a warp-uniform scalar update: the scan is exact per anti-diagonal,
+// so a terminated alignment stops at once and the warp pulls the next job (work redistribution on termination).
+// Per cell: IDP.4A (score lookup + add), IADD, VIMNMX3, 2x VIADDMNMX, LEA, 1/2 VIMNMX3  -- DPX max-plus ops on
+// the ALU pipe, the rest on the FMA pipe.
+#pragma once
+
+#include <cstdint>
+#include <climits>
+#include <type_traits>
+#include <cuda_runtime.h>
+
+#include "agatha_b200.h"
+
+namespace agatha {
+
+constexpr int NEG16 = -16384;        // the reference's MINUS_INF2 (gasal_kernels.h:39); exact value matters for parity
+constexpr int NEGBIG = -(1 << 25);   // "never a real score"; NEGBIG*32 still fits int32 (tracking keys)
+constexpr unsigned FULL = 0xffffffffu;
+
+// canonical 4-bit codes written by the pack kernel (pack_kernel.cuh)
+constexpr int QCODE_N = 4;           // query  'N'
+constexpr int TCODE_N = 13;          // target 'N'   (4 ^ 13 = 9, (0..3) ^ 13 = 12..15: all hit sign-replicated LUT entries)
+constexpr int QCODE_Y = 13;          // the one non-ACGTN symbol whose query code collides with TCODE_N ...
+constexpr int TCODE_Y = 4;           // ... and its target code
+
+struct KernelParams {
+    int match, mismatch, goe, ge, sw, Z, W;
+    unsigned tab_lo, tab_hi;         // PRMT lookup table: byte x -> score for code XOR x (fast alphabet)
+    int LW, JW;                      // lane / cell index of k = +W  (global cell index g = W, u = 0)
+};
+
+struct JobArrays {
+    const uint32_t* qpk;             // query  bases, 8 per word, first base in bits 31..28, codes cq()
+    const uint32_t* tpk;             // target bases, 8 per word, first base in bits  3..0,  codes ct()
+    const uint32_t* qoff_w;          // word offset of each query in qpk
+    const uint32_t* toff_w;
+    const uint32_t* qlen;            // in bases
+    const uint32_t* tlen;
+    const uint32_t* order;           // job -> pair index, longest first (host-side bucketing), may be null
+    int32_t* score;
+    int32_t* qend;
+    int32_t* tend;
+    int32_t* stop;                   // AGATHA_STOP_*
+    int32_t* dstop;
+    unsigned* counter;               // work queue head
+    int n;
+};
+
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel)
+{
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One anti-diagonal step for the C cells of parity U owned by this lane.
+//   H   : H of the parity-U cells (value from anti-diagonal d-2 on entry, d on exit)
+//   E,F : on entry outputs of the previous step (other parity); on exit outputs of this step
+//   Qw/Rw: nibble j of the windows holds the query/target code of cell j
+// Returns the lane's best tracking key max_j(H_j*32 + j) (ties -> largest j == largest target index).
+// Recurrence: CORE_COMPUTE, agatha_kernel.h:20-30 (gap opens from M = diag + s, not from H).
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, int U, bool TAIL, bool GENERIC>
+__device__ __forceinline__ int step_cells(int (&H)[C], int (&E)[C], int (&F)[C],
+                                          const uint32_t (&Qw)[(C + 7) / 8], const uint32_t (&Rw)[(C + 7) / 8],
+                                          int edge_in, const KernelParams& p, int jlo, int jhi)
+{
+    constexpr int NWORD = (C + 7) / 8;
+    unsigned sc[2 * NWORD];
+    if (!GENERIC) {
+#pragma unroll
+        for (int w = 0; w < NWORD; w++) {
+            unsigned x = Qw[w] ^ Rw[w];
+            sc[2 * w] = prmt(p.tab_lo, p.tab_hi, x);
+            sc[2 * w + 1] = prmt(p.tab_lo, p.tab_hi, x >> 16);
+        }
+    }
+    const int mge = -p.ge, mgoe = -p.goe;
+    int best = INT_MIN;
+    int pend = INT_MIN;
+
+#pragma unroll
+    for (int jj = 0; jj < C; jj++) {
+        // U == 0 reads E[j-1] (old) -> walk j downwards; U == 1 reads F[j+1] (old) -> walk j upwards
+        const int j = (U == 0) ? (C - 1 - jj) : jj;
+        int ein, fin;
+        if (U == 0) { ein = (j == 0) ? edge_in : E[j - 1]; fin = F[j]; }
+        else        { ein = E[j]; fin = (j == C - 1) ? edge_in : F[j + 1]; }
+        int m;
+        if (!GENERIC) {
+            m = __dp4a((int)sc[j >> 2], 1 << (8 * (j & 3)), H[j]);                 // H(d-2,k) + s
+        } else {
+            const unsigned a = (Qw[j >> 3] >> (4 * (j & 7))) & 15u, b = (Rw[j >> 3] >> (4 * (j & 7))) & 15u;
+            const bool isn = (a == (unsigned)QCODE_N) | (b == (unsigned)TCODE_N);
+            const bool eq = (a == b) | ((a == (unsigned)QCODE_Y) & (b == (unsigned)TCODE_Y));
+            const int s = isn ? -1 : (eq ? p.match : -p.mismatch);                // DEV_GET_SUB_SCORE_GLOBAL, N_PENALTY=1
+            m = H[j] + s;
+        }
+        const int h = __vimax3_s32(m, ein, fin);
+        const int t = m + mgoe;
+        E[j] = __viaddmax_s32(ein, mge, t);
+        F[j] = __viaddmax_s32(fin, mge, t);
+        H[j] = h;
+        int key = h * 32 + j;
+        if (TAIL) key = (j >= jlo && j <= jhi) ? key : INT_MIN;
+        if (jj & 1) best = __vimax3_s32(best, pend, key); else pend = key;
+    }
+    if (C & 1) best = max(best, pend);
+    return best;
+}
+
+// Write `val` to arr[idx] with a run-time idx while keeping arr in registers: every case is a static index, and the
+// switch compiles to a jump, so the single lane that executes it pays a few instructions instead of C predicated moves.
+template <int C>
+__device__ __forceinline__ void poke(int (&arr)[C], int idx, int val)
+{
+#define AGATHA_POKE_CASE(J) case J: if (J < C) arr[(J) < C ? (J) : 0] = val; break;
+    switch (idx) {
+        AGATHA_POKE_CASE(0)  AGATHA_POKE_CASE(1)  AGATHA_POKE_CASE(2)  AGATHA_POKE_CASE(3)
+        AGATHA_POKE_CASE(4)  AGATHA_POKE_CASE(5)  AGATHA_POKE_CASE(6)  AGATHA_POKE_CASE(7)
+        AGATHA_POKE_CASE(8)  AGATHA_POKE_CASE(9)  AGATHA_POKE_CASE(10) AGATHA_POKE_CASE(11)
+        AGATHA_POKE_CASE(12) AGATHA_POKE_CASE(13) AGATHA_POKE_CASE(14) AGATHA_POKE_CASE(15)
+        AGATHA_POKE_CASE(16) AGATHA_POKE_CASE(17) AGATHA_POKE_CASE(18) AGATHA_POKE_CASE(19)
+        AGATHA_POKE_CASE(20) AGATHA_POKE_CASE(21) AGATHA_POKE_CASE(22) AGATHA_POKE_CASE(23)
+        AGATHA_POKE_CASE(24) AGATHA_POKE_CASE(25) AGATHA_POKE_CASE(26) AGATHA_POKE_CASE(27)
+        AGATHA_POKE_CASE(28) AGATHA_POKE_CASE(29) AGATHA_POKE_CASE(30) AGATHA_POKE_CASE(31)
+        default: break;
+    }
+#undef AGATHA_POKE_CASE
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Everything about one alignment that is uniform across the warp.
+// ---------------------------------------------------------------------------------------------------------------
+struct Pair {
+    const uint32_t* q;   // packed query words of this pair
+    const uint32_t* t;
+    int qlen, tlen, qwords, twords, pq, pt, tcols, total, L;
+};
+
+__device__ __forceinline__ uint32_t load_qword(const Pair& pr, int wi)
+{
+    return (wi >= 0 && wi < pr.qwords) ? __ldg(pr.q + wi) : 0u;
+}
+__device__ __forceinline__ uint32_t load_tword(const Pair& pr, int wi)
+{
+    return (wi >= 0 && wi < pr.twords) ? __ldg(pr.t + wi) : 0xddddddddu;   // TCODE_N everywhere
+}
+__device__ __forceinline__ unsigned qbase(const Pair& pr, int i)   // code of query[i], 0 outside
+{
+    if (i < 0 || i >= pr.qwords * 8) return 0u;
+    return (__ldg(pr.q + (i >> 3)) >> (28 - 4 * (i & 7))) & 15u;
+}
+__device__ __forceinline__ unsigned tbase(const Pair& pr, int i)
+{
+    if (i < 0 || i >= pr.twords * 8) return (unsigned)TCODE_N;
+    return (__ldg(pr.t + (i >> 3)) >> (4 * (i & 7))) & 15u;
+}
+
+// true when the pair holds a symbol outside {A,C,G,T,N}: the PRMT lookup table cannot score those
+__device__ __forceinline__ bool has_rare_symbols(const Pair& pr, int lane)
+{
+    bool rare = false;
+    for (int i = lane; i < pr.qwords; i += 32) {
+        const uint32_t w = __ldg(pr.q + i);
+        // nibble > 4  <=>  bit3 | (bit2 & (bit1|bit0))
+        const uint32_t b3 = w & 0x88888888u, b2 = w & 0x44444444u, lo = ((w << 1) | (w << 2)) & 0x44444444u;
+        rare |= (b3 | (b2 & lo)) != 0u;
+    }
+    for (int i = lane; i < pr.twords; i += 32) {
+        const uint32_t w = __ldg(pr.t + i);
+        // nibble in {0,1,2,3} or == 13 is fine
+        const uint32_t hi = (w | (w >> 1)) & 0x44444444u;                 // bit2 set <=> nibble >= 4 (bit3|bit2)
+        const uint32_t x = w ^ 0xddddddddu;                               // nibble == 0 <=> code 13
+        const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;   // 1 <=> nibble != 13
+        rare |= ((hi >> 2) & nz) != 0u;
+    }
+    return __any_sync(FULL, rare);
+}
+
+struct ScanState { int max, mt, mq; };
+
+// Termination Condition & Score Update for one anti-diagonal (agatha_kernel.h:292-314), warp-uniform.
+// `best` is this lane's key from step_cells. Returns true when Z-drop fires.
+template <int C>
+__device__ __forceinline__ bool scan_diag(ScanState& st, int best, int d, int u, int lane, const KernelParams& p)
+{
+    const int v = best >> 5;
+    int hmax = __reduce_max_sync(FULL, v);
+    const bool newmax = hmax > st.max;
+    if (!newmax && (p.Z < 0 || (p.ge >= 0 && st.max - hmax <= p.Z))) return false;   // cannot fire: l*ge >= 0
+    int r;
+    if (hmax < -32768) {                 // empty ring slot reads as INT_MIN -> (h,r) = (-32768, 0), :152,:296-299
+        hmax = -32768; r = 0;
+    } else {
+        const unsigned who = __ballot_sync(FULL, v == hmax);
+        const int src = 31 - __clz((int)who);                                        // ties -> largest target index
+        const int jb = __shfl_sync(FULL, best & 31, src);
+        const int k = -p.W + 2 * (C * src + jb) + u;
+        r = (d + k) >> 1;
+    }
+    if (hmax > st.max) { st.max = hmax; st.mt = r; st.mq = d - r; return false; }
+    if (r >= st.mt && d - r >= st.mq) {
+        const int tl = r - st.mt, ql = (d - r) - st.mq;
+        const int l = tl > ql ? tl - ql : ql - tl;
+        if (p.Z >= 0 && st.max - hmax > p.Z + l * p.ge) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One alignment, one warp.  WODD = (W & 1): fixes which parity class the even anti-diagonals use.
+// ---------------------------------------------------------------------------------------------------------------
+// JWS >= 0: the cell index of k = +W inside its lane is known at compile time (W % C == JWS); -1: run-time.
+template <int C, bool WODD, int JWS, bool GENERIC>
+__device__ __noinline__ void run_pair(const Pair& pr, const KernelParams& p, int lane,
+                                      int& out_score, int& out_qend, int& out_tend, int& out_stop, int& out_dstop)
+{
+    static_assert(C % 8 == 0 && C <= 32, "cells per lane must be a multiple of 8");
+    constexpr int NWORD = (C + 7) / 8;
+    const int W = p.W;
+
+    int H0[C], H1[C], E[C], F[C];
+#pragma unroll
+    for (int j = 0; j < C; j++) { H0[j] = NEGBIG; H1[j] = NEGBIG; E[j] = NEGBIG; F[j] = NEGBIG; }
+
+    // --- sequence windows at d = 0: nibble j <-> query[qtop - j], target[rbot + j] ---------------------------
+    int qtop = (W >> 1) - C * lane;                 // ((d+W)>>1) - C*lane at d = 0
+    int rbot = ((1 - W) >> 1) + C * lane;           // ((d-W+1)>>1) + C*lane at d = 0
+    uint32_t Qw[NWORD], Rw[NWORD];
+#pragma unroll
+    for (int w = 0; w < NWORD; w++) { Qw[w] = 0u; Rw[w] = 0u; }
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        Qw[j >> 3] |= qbase(pr, qtop - j) << (4 * (j & 7));
+        Rw[j >> 3] |= tbase(pr, rbot + j) << (4 * (j & 7));
+    }
+    // feeds: next query base in the top nibble of qfeed, next target base in the bottom nibble of rfeed
+    uint32_t qfeed, rfeed;
+    {
+        const int nq = qtop + 1, nb = rbot + C;
+        qfeed = load_qword(pr, nq >> 3) << (4 * (nq & 7));
+        rfeed = load_tword(pr, nb >> 3) >> (4 * (nb & 7));
+    }
+
+    // --- boundary: H(-1,-1) = 0, then the virtual cells of "anti-diagonal -1" (agatha_kernel.h:126-148) -------
+    // cell (g,u) of global lane index: k = -W + 2g + u.
+    auto inject = [&](int d, int u) {
+        // virtual cells of anti-diagonal d: (q=-1, r=d+1) at k = d+2 and (q=d+1, r=-1) at k = -(d+2);
+        // values H(-1,j) = H(j,-1) = -(goe + ge*j), F(0,j) = E(j,0) = that - goe, for j <= W.
+        const int jv = d + 1;
+        if (jv > W) return;
+        const int hv = -(p.goe + p.ge * jv), gv = hv - p.goe;
+        {   // top: consumer (0, d+1) reads F; (0, d+2) reads H as its diagonal
+            const int g = (d + 2 + W) >> 1;
+            const int ln = g / C, j = g - ln * C;
+            if (lane == ln) {
+                const bool in_band = (d + 2) <= W;
+                if (u == 0) { if (in_band) poke<C>(H0, j, hv); } else { if (in_band) poke<C>(H1, j, hv); }
+                poke<C>(F, j, gv);
+            }
+        }
+        if (W - d - 2 >= 0) {   // left: consumer (d+1, 0) reads E; (d+2, 0) reads H as its diagonal
+            const int g = (W - d - 2) >> 1;
+            const int ln = g / C, j = g - ln * C;
+            if (lane == ln) {
+                if (u == 0) poke<C>(H0, j, hv); else poke<C>(H1, j, hv);
+                poke<C>(E, j, gv);
+            }
+        }
+    };
+    {
+        const int g = W >> 1;                       // k = 0: 2g + u = W, u = W & 1
+        const int ln = g / C, j = g - ln * C;
+        if (lane == ln) { if (WODD) poke<C>(H1, j, 0); else poke<C>(H0, j, 0); }
+        inject(-1, WODD ? 0 : 1);                   // u(-1) = (W-1) & 1
+    }
+
+    ScanState st = {0, 0, 0};                        // agatha_kernel.h:158-161
+    int stop = AGATHA_STOP_END, d_stop = pr.L;
+    const int d_tail = min(2 * pr.qlen - 2 - W, 2 * pr.tcols - 2 - W) + 1;   // first d whose valid k-range is clipped by the far edges
+    const bool has_phantom = pr.tcols > pr.tlen;
+    const bool edge_lane = (lane == p.LW);
+
+    // phantom (padding) target columns: their F and diagonal inputs restart from MINUS_INF2 at the first row of every
+    // slice chunk of the last target block (agatha_kernel.h:206-221 reload, :272-279 never stored); see oracle.
+    auto phantom_patch = [&](int d, int u) {
+        const int qc = (d - pr.tlen) & ~7;           // the only multiple of 8 in (d - tcols, d - tlen]
+        if (d - pr.tlen < 0 || d - qc >= pr.tcols || qc >= pr.qlen) return;
+        if (!(qc == 0 || ((qc >> 3) + pr.pt - 1) % p.sw == 0)) return;
+        const int r = d - qc, k = r - qc;
+        if (k > W || k < -W) return;
+        const int g = (k + W - u) >> 1;              // cell (g,u) itself
+        // F input of cell (g,u): U==0 reads F[j] ; U==1 reads F[j+1] (or the next lane's F[0])
+        const int gf = (u == 0) ? g : g + 1;
+        const int lnf = gf / C, jf = gf - lnf * C;
+        if (lane == lnf) poke<C>(F, jf, NEG16);
+        if (r - 1 >= pr.tlen) {
+            const int ln = g / C, j = g - ln * C;
+            if (lane == ln) { if (u == 0) poke<C>(H0, j, NEG16); else poke<C>(H1, j, NEG16); }
+        }
+    };
+
+    auto valid_range = [&](int d, int u, int& jlo, int& jhi) {
+        const int klo = max(-W, max(-d, d - 2 * (pr.qlen - 1)));
+        const int khi = min(W, min(d, 2 * (pr.tcols - 1) - d));
+        const int k0 = -W + 2 * C * lane + u;
+        // j >= ceil((klo-k0)/2), j <= floor((khi-k0)/2)
+        jlo = (klo - k0 + 1) >> 1;
+        jhi = (khi - k0) >> 1;
+    };
+
+    auto shift_query = [&]() {                       // qtop -> qtop + 1
+        const int nq = qtop + 1;
+        if ((nq & 7) == 0) qfeed = load_qword(pr, nq >> 3);
+#pragma unroll
+        for (int w = NWORD - 1; w > 0; w--) Qw[w] = __funnelshift_l(Qw[w - 1], Qw[w], 4);
+        Qw[0] = __funnelshift_l(qfeed, Qw[0], 4);
+        qfeed <<= 4;
+        qtop = nq;
+    };
+    auto shift_ref = [&]() {                         // rbot -> rbot + 1
+        const int nb = rbot + C;
+        if ((nb & 7) == 0) rfeed = load_tword(pr, nb >> 3);
+#pragma unroll
+        for (int w = 0; w < NWORD - 1; w++) Rw[w] = __funnelshift_r(Rw[w], Rw[w + 1], 4);
+        Rw[NWORD - 1] = __funnelshift_r(Rw[NWORD - 1], rfeed, 4);
+        rfeed >>= 4;
+        rbot++;
+    };
+
+    // one anti-diagonal: returns true when the alignment must stop (Z-drop)
+    auto do_step = [&](int d, bool scan, bool tail, auto u_tag) -> bool {
+        constexpr int U = decltype(u_tag)::value;
+        int jlo = 0, jhi = C - 1;
+        if (tail) { valid_range(d, U, jlo, jhi); if (has_phantom) phantom_patch(d, U); }
+        int best;
+        if (U == 0) {
+            int ein = __shfl_up_sync(FULL, E[C - 1], 1);
+            // k = -W: left of it is outside the band (MINUS_INF2), except on the matrix edge where E(W,0) is a boundary
+            // value (agatha_kernel.h:130); before the band edge enters the matrix the cell is not real: keep it dead
+            if (lane == 0) ein = (d > W) ? NEG16 : ((d == W) ? (-(p.goe + p.ge * W) - p.goe) : NEGBIG);
+            best = tail ? step_cells<C, 0, true, GENERIC>(H0, E, F, Qw, Rw, ein, p, jlo, jhi)
+                        : step_cells<C, 0, false, GENERIC>(H0, E, F, Qw, Rw, ein, p, jlo, jhi);
+            if (edge_lane) { if (JWS >= 0) E[JWS >= 0 ? JWS : 0] = NEGBIG; else poke<C>(E, p.JW, NEGBIG); }   // nothing may leak into k = W+1
+            shift_ref();
+        } else {
+            int fin = __shfl_down_sync(FULL, F[0], 1);
+            if (lane == 31) fin = NEGBIG;
+            best = tail ? step_cells<C, 1, true, GENERIC>(H1, E, F, Qw, Rw, fin, p, jlo, jhi)
+                        : step_cells<C, 1, false, GENERIC>(H1, E, F, Qw, Rw, fin, p, jlo, jhi);
+            // k = W reads MINUS_INF2 from outside the band (agatha_kernel.h:138); F(0,W) is injected below at d = W-1
+            if (edge_lane) { const int v = (d + 1 > W) ? NEG16 : NEGBIG; if (JWS >= 0) F[JWS >= 0 ? JWS : 0] = v; else poke<C>(F, p.JW, v); }
+            shift_query();
+        }
+        if (d < W) inject(d, U);
+        if (!scan) return false;
+        return scan_diag<C>(st, best, d, U, lane, p);
+    };
+    using U0 = std::integral_constant<int, 0>;
+    using U1 = std::integral_constant<int, 1>;
+
+    // --- the slice schedule of the reference (agatha_kernel.h:180-330), replayed per anti-diagonal ----------------
+    int d = 0, i = 0;
+    bool done = false;
+    for (i = 0; i < pr.total && !done; i += p.sw) {
+        // slice bounds, agatha_kernel.h:183-191 (truncating division as in the reference)
+        int ss = max(0, i - pr.pq + 1);
+        ss = max(ss, (i * 8 + 8 - W) / 2 / 8);
+        int se = min(pr.pt - 1, i + p.sw - 1);
+        se = min(se, ((i + p.sw - 1) * 8 + 7 + W) / 2 / 8);
+        if (ss > se) { stop = AGATHA_STOP_BANDEXIT; d_stop = min(8 * i, pr.L); done = true; break; }
+        const int dend = 8 * (i + p.sw);
+        for (; d < dend; d += 2) {
+            const bool tail = (d + 1 >= d_tail);
+            bool z;
+            if (WODD) z = do_step(d, d < pr.L, tail, U1{}); else z = do_step(d, d < pr.L, tail, U0{});
+            if (z) { stop = AGATHA_STOP_ZDROP; d_stop = d + 1; done = true; break; }
+            if (WODD) z = do_step(d + 1, d + 1 < pr.L, tail, U0{}); else z = do_step(d + 1, d + 1 < pr.L, tail, U1{});
+            if (z) { stop = AGATHA_STOP_ZDROP; d_stop = d + 2; done = true; break; }
+        }
+    }
+    // job wrap-up, agatha_kernel.h:334-356: 8 more anti-diagonals are scanned (without the d < L guard) when the
+    // slice loop ended exactly on total_anti_diags; otherwise those ring slots are empty (see oracle).
+    if (!done && i == pr.total) {
+        const int dend = 8 * pr.total + 8;
+        for (; d < dend && !done; d += 2) {
+            bool z;
+            if (WODD) z = do_step(d, true, true, U1{}); else z = do_step(d, true, true, U0{});
+            if (z) { if (d < pr.L) { stop = AGATHA_STOP_ZDROP; d_stop = d + 1; } break; }
+            if (WODD) z = do_step(d + 1, true, true, U0{}); else z = do_step(d + 1, true, true, U1{});
+            if (z) { if (d + 1 < pr.L) { stop = AGATHA_STOP_ZDROP; d_stop = d + 2; } break; }
+        }
+    }
+    out_score = st.max; out_qend = st.mq; out_tend = st.mt; out_stop = stop; out_dstop = d_stop;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent kernel: every warp pulls alignments from a queue ordered longest-first by the host scheduler.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, bool WODD, int JWS>
+__global__ void __launch_bounds__(128, 3) extend_kernel(JobArrays ja, KernelParams p)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned job = 0;
+        if (lane == 0) job = atomicAdd(ja.counter, 1u);
+        job = __shfl_sync(FULL, job, 0);
+        if (job >= (unsigned)ja.n) break;
+        const unsigned idx = ja.order ? __ldg(ja.order + job) : job;
+
+        Pair pr;
+        pr.qlen = (int)__ldg(ja.qlen + idx);
+        pr.tlen = (int)__ldg(ja.tlen + idx);
+        pr.q = ja.qpk + (__ldg(ja.qoff_w + idx) >> 3);     // offsets are in bases, multiples of 8 (agatha_kernel.h:116-117)
+        pr.t = ja.tpk + (__ldg(ja.toff_w + idx) >> 3);
+        pr.pq = (pr.qlen + 7) >> 3; pr.pt = (pr.tlen + 7) >> 3;        // agatha_kernel.h:120-121
+        pr.qwords = pr.pq; pr.twords = pr.pt;
+        pr.tcols = 8 * pr.pt;
+        pr.total = pr.pq + pr.pt - 1;                                  // :165
+        pr.L = pr.qlen + pr.tlen - 1;                                  // :289
+
+        int score = 0, qend = 0, tend = 0, stop = AGATHA_STOP_END, dstop = 0;
+        if (pr.qlen > 0 && pr.tlen > 0) {
+            if (has_rare_symbols(pr, lane)) run_pair<C, WODD, JWS, true>(pr, p, lane, score, qend, tend, stop, dstop);
+            else run_pair<C, WODD, JWS, false>(pr, p, lane, score, qend, tend, stop, dstop);
+        }
+        if (lane == 0) {
+            ja.score[idx] = score; ja.qend[idx] = qend; ja.tend[idx] = tend;   // agatha_kernel.h:359-363
+            if (ja.stop) ja.stop[idx] = stop;
+            if (ja.dstop) ja.dstop[idx] = dstop;
+        }
+    }
+}
+
+}  // namespace agatha
