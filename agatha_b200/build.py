@@ -36,7 +36,8 @@ def _sources():
 def _digest():
     h = hashlib.sha256()
     files = sorted([os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h"))])
-    files += [os.path.join(ROOT, "include", f) for f in sorted(os.listdir(os.path.join(ROOT, "include")))]
+    for dp, _, fns in sorted(os.walk(os.path.join(ROOT, "include"))):
+        files += [os.path.join(dp, f) for f in sorted(fns)]
     for f in files:
         h.update(f.encode())
         with open(f, "rb") as fh:

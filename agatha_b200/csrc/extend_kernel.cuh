@@ -224,14 +224,22 @@ __device__ __forceinline__ bool scan_diag(ScanState& st, int best, int d, int u,
 
 // ---------------------------------------------------------------------------------------------------------------
 // One alignment, one warp.  WODD = (W & 1): fixes which parity class the even anti-diagonals use.
-// ---------------------------------------------------------------------------------------------------------------
 // JWS >= 0: the cell index of k = +W inside its lane is known at compile time (W % C == JWS); -1: run-time.
+//
+// Two loop bodies only, so that the steady state stays small and branch-free:
+//   FAST  anti-diagonals W < d < d_tail: every lane's cells are inside the matrix, nothing to inject or mask
+//   SLOW  everything else: matrix-edge injection (d < W), far-edge masking, padding-column patch, wrap-up
+// ---------------------------------------------------------------------------------------------------------------
 template <int C, bool WODD, int JWS, bool GENERIC>
-__device__ __noinline__ void run_pair(const Pair& pr, const KernelParams& p, int lane,
-                                      int& out_score, int& out_qend, int& out_tend, int& out_stop, int& out_dstop)
+__device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, int lane,
+                                         int& out_score, int& out_qend, int& out_tend, int& out_stop, int& out_dstop)
 {
     static_assert(C % 8 == 0 && C <= 32, "cells per lane must be a multiple of 8");
-    constexpr int NWORD = (C + 7) / 8;
+    constexpr int NWORD = C / 8;
+    using U0 = std::integral_constant<int, 0>;
+    using U1 = std::integral_constant<int, 1>;
+    using UA = std::integral_constant<int, WODD ? 1 : 0>;   // parity class of even anti-diagonals
+    using UB = std::integral_constant<int, WODD ? 0 : 1>;   // ... of odd ones
     const int W = p.W;
 
     int H0[C], H1[C], E[C], F[C];
@@ -244,10 +252,11 @@ __device__ __noinline__ void run_pair(const Pair& pr, const KernelParams& p, int
     uint32_t Qw[NWORD], Rw[NWORD];
 #pragma unroll
     for (int w = 0; w < NWORD; w++) { Qw[w] = 0u; Rw[w] = 0u; }
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < C; j++) {
-        Qw[j >> 3] |= qbase(pr, qtop - j) << (4 * (j & 7));
-        Rw[j >> 3] |= tbase(pr, rbot + j) << (4 * (j & 7));
+        const unsigned qb = qbase(pr, qtop - j) << (4 * (j & 7)), tb = tbase(pr, rbot + j) << (4 * (j & 7));
+#pragma unroll
+        for (int w = 0; w < NWORD; w++) if (w == (j >> 3)) { Qw[w] |= qb; Rw[w] |= tb; }
     }
     // feeds: next query base in the top nibble of qfeed, next target base in the bottom nibble of rfeed
     uint32_t qfeed, rfeed;
@@ -258,10 +267,10 @@ __device__ __noinline__ void run_pair(const Pair& pr, const KernelParams& p, int
     }
 
     // --- boundary: H(-1,-1) = 0, then the virtual cells of "anti-diagonal -1" (agatha_kernel.h:126-148) -------
-    // cell (g,u) of global lane index: k = -W + 2g + u.
-    auto inject = [&](int d, int u) {
-        // virtual cells of anti-diagonal d: (q=-1, r=d+1) at k = d+2 and (q=d+1, r=-1) at k = -(d+2);
-        // values H(-1,j) = H(j,-1) = -(goe + ge*j), F(0,j) = E(j,0) = that - goe, for j <= W.
+    // virtual cells of anti-diagonal d: (q=-1, r=d+1) at k = d+2 and (q=d+1, r=-1) at k = -(d+2);
+    // values H(-1,j) = H(j,-1) = -(goe + ge*j), F(0,j) = E(j,0) = that - goe, for j <= W.  (cell (g,u): k = -W + 2g + u)
+    auto inject = [&](int d, auto u_tag) {
+        constexpr int U = decltype(u_tag)::value;
         const int jv = d + 1;
         if (jv > W) return;
         const int hv = -(p.goe + p.ge * jv), gv = hv - p.goe;
@@ -269,8 +278,7 @@ __device__ __noinline__ void run_pair(const Pair& pr, const KernelParams& p, int
             const int g = (d + 2 + W) >> 1;
             const int ln = g / C, j = g - ln * C;
             if (lane == ln) {
-                const bool in_band = (d + 2) <= W;
-                if (u == 0) { if (in_band) poke<C>(H0, j, hv); } else { if (in_band) poke<C>(H1, j, hv); }
+                if ((d + 2) <= W) { if (U == 0) poke<C>(H0, j, hv); else poke<C>(H1, j, hv); }
                 poke<C>(F, j, gv);
             }
         }
@@ -278,7 +286,7 @@ __device__ __noinline__ void run_pair(const Pair& pr, const KernelParams& p, int
             const int g = (W - d - 2) >> 1;
             const int ln = g / C, j = g - ln * C;
             if (lane == ln) {
-                if (u == 0) poke<C>(H0, j, hv); else poke<C>(H1, j, hv);
+                if (U == 0) poke<C>(H0, j, hv); else poke<C>(H1, j, hv);
                 poke<C>(E, j, gv);
             }
         }
@@ -287,41 +295,31 @@ __device__ __noinline__ void run_pair(const Pair& pr, const KernelParams& p, int
         const int g = W >> 1;                       // k = 0: 2g + u = W, u = W & 1
         const int ln = g / C, j = g - ln * C;
         if (lane == ln) { if (WODD) poke<C>(H1, j, 0); else poke<C>(H0, j, 0); }
-        inject(-1, WODD ? 0 : 1);                   // u(-1) = (W-1) & 1
+        inject(-1, UB{});                           // u(-1) = (W-1) & 1
     }
 
     ScanState st = {0, 0, 0};                        // agatha_kernel.h:158-161
     int stop = AGATHA_STOP_END, d_stop = pr.L;
-    const int d_tail = min(2 * pr.qlen - 2 - W, 2 * pr.tcols - 2 - W) + 1;   // first d whose valid k-range is clipped by the far edges
     const bool has_phantom = pr.tcols > pr.tlen;
     const bool edge_lane = (lane == p.LW);
 
     // phantom (padding) target columns: their F and diagonal inputs restart from MINUS_INF2 at the first row of every
     // slice chunk of the last target block (agatha_kernel.h:206-221 reload, :272-279 never stored); see oracle.
-    auto phantom_patch = [&](int d, int u) {
+    auto phantom_patch = [&](int d, auto u_tag) {
+        constexpr int U = decltype(u_tag)::value;
         const int qc = (d - pr.tlen) & ~7;           // the only multiple of 8 in (d - tcols, d - tlen]
         if (d - pr.tlen < 0 || d - qc >= pr.tcols || qc >= pr.qlen) return;
         if (!(qc == 0 || ((qc >> 3) + pr.pt - 1) % p.sw == 0)) return;
         const int r = d - qc, k = r - qc;
         if (k > W || k < -W) return;
-        const int g = (k + W - u) >> 1;              // cell (g,u) itself
-        // F input of cell (g,u): U==0 reads F[j] ; U==1 reads F[j+1] (or the next lane's F[0])
-        const int gf = (u == 0) ? g : g + 1;
+        const int g = (k + W - U) >> 1;              // cell (g,U) itself
+        const int gf = (U == 0) ? g : g + 1;         // its F input: U==0 reads F[j], U==1 reads F[j+1] / next lane's F[0]
         const int lnf = gf / C, jf = gf - lnf * C;
         if (lane == lnf) poke<C>(F, jf, NEG16);
         if (r - 1 >= pr.tlen) {
             const int ln = g / C, j = g - ln * C;
-            if (lane == ln) { if (u == 0) poke<C>(H0, j, NEG16); else poke<C>(H1, j, NEG16); }
+            if (lane == ln) { if (U == 0) poke<C>(H0, j, NEG16); else poke<C>(H1, j, NEG16); }
         }
-    };
-
-    auto valid_range = [&](int d, int u, int& jlo, int& jhi) {
-        const int klo = max(-W, max(-d, d - 2 * (pr.qlen - 1)));
-        const int khi = min(W, min(d, 2 * (pr.tcols - 1) - d));
-        const int k0 = -W + 2 * C * lane + u;
-        // j >= ceil((klo-k0)/2), j <= floor((khi-k0)/2)
-        jlo = (klo - k0 + 1) >> 1;
-        jhi = (khi - k0) >> 1;
     };
 
     auto shift_query = [&]() {                       // qtop -> qtop + 1
@@ -343,68 +341,82 @@ __device__ __noinline__ void run_pair(const Pair& pr, const KernelParams& p, int
         rbot++;
     };
 
-    // one anti-diagonal: returns true when the alignment must stop (Z-drop)
-    auto do_step = [&](int d, bool scan, bool tail, auto u_tag) -> bool {
+    // one anti-diagonal; returns true when Z-drop fires on it
+    auto do_step = [&](int d, bool scan, auto u_tag, auto fast_tag) -> bool {
         constexpr int U = decltype(u_tag)::value;
+        constexpr bool FAST = decltype(fast_tag)::value;
         int jlo = 0, jhi = C - 1;
-        if (tail) { valid_range(d, U, jlo, jhi); if (has_phantom) phantom_patch(d, U); }
+        if (!FAST) {
+            const int klo = max(-W, max(-d, d - 2 * (pr.qlen - 1)));
+            const int khi = min(W, min(d, 2 * (pr.tcols - 1) - d));
+            const int k0 = -W + 2 * C * lane + U;
+            jlo = (klo - k0 + 1) >> 1;               // ceil((klo-k0)/2)
+            jhi = (khi - k0) >> 1;
+            if (has_phantom) phantom_patch(d, u_tag);
+        }
         int best;
         if (U == 0) {
             int ein = __shfl_up_sync(FULL, E[C - 1], 1);
             // k = -W: left of it is outside the band (MINUS_INF2), except on the matrix edge where E(W,0) is a boundary
             // value (agatha_kernel.h:130); before the band edge enters the matrix the cell is not real: keep it dead
-            if (lane == 0) ein = (d > W) ? NEG16 : ((d == W) ? (-(p.goe + p.ge * W) - p.goe) : NEGBIG);
-            best = tail ? step_cells<C, 0, true, GENERIC>(H0, E, F, Qw, Rw, ein, p, jlo, jhi)
-                        : step_cells<C, 0, false, GENERIC>(H0, E, F, Qw, Rw, ein, p, jlo, jhi);
+            if (lane == 0) ein = (FAST || d > W) ? NEG16 : ((d == W) ? (-(p.goe + p.ge * W) - p.goe) : NEGBIG);
+            best = step_cells<C, 0, !FAST, GENERIC>(H0, E, F, Qw, Rw, ein, p, jlo, jhi);
             if (edge_lane) { if (JWS >= 0) E[JWS >= 0 ? JWS : 0] = NEGBIG; else poke<C>(E, p.JW, NEGBIG); }   // nothing may leak into k = W+1
             shift_ref();
         } else {
             int fin = __shfl_down_sync(FULL, F[0], 1);
             if (lane == 31) fin = NEGBIG;
-            best = tail ? step_cells<C, 1, true, GENERIC>(H1, E, F, Qw, Rw, fin, p, jlo, jhi)
-                        : step_cells<C, 1, false, GENERIC>(H1, E, F, Qw, Rw, fin, p, jlo, jhi);
+            best = step_cells<C, 1, !FAST, GENERIC>(H1, E, F, Qw, Rw, fin, p, jlo, jhi);
             // k = W reads MINUS_INF2 from outside the band (agatha_kernel.h:138); F(0,W) is injected below at d = W-1
-            if (edge_lane) { const int v = (d + 1 > W) ? NEG16 : NEGBIG; if (JWS >= 0) F[JWS >= 0 ? JWS : 0] = v; else poke<C>(F, p.JW, v); }
+            if (edge_lane) { const int v = (FAST || d + 1 > W) ? NEG16 : NEGBIG; if (JWS >= 0) F[JWS >= 0 ? JWS : 0] = v; else poke<C>(F, p.JW, v); }
             shift_query();
         }
-        if (d < W) inject(d, U);
+        if (!FAST) { if (d < W) inject(d, u_tag); }
         if (!scan) return false;
         return scan_diag<C>(st, best, d, U, lane, p);
     };
-    using U0 = std::integral_constant<int, 0>;
-    using U1 = std::integral_constant<int, 1>;
 
     // --- the slice schedule of the reference (agatha_kernel.h:180-330), replayed per anti-diagonal ----------------
-    int d = 0, i = 0;
-    bool done = false;
-    for (i = 0; i < pr.total && !done; i += p.sw) {
-        // slice bounds, agatha_kernel.h:183-191 (truncating division as in the reference)
-        int ss = max(0, i - pr.pq + 1);
-        ss = max(ss, (i * 8 + 8 - W) / 2 / 8);
-        int se = min(pr.pt - 1, i + p.sw - 1);
-        se = min(se, ((i + p.sw - 1) * 8 + 7 + W) / 2 / 8);
-        if (ss > se) { stop = AGATHA_STOP_BANDEXIT; d_stop = min(8 * i, pr.L); done = true; break; }
-        const int dend = 8 * (i + p.sw);
-        for (; d < dend; d += 2) {
-            const bool tail = (d + 1 >= d_tail);
-            bool z;
-            if (WODD) z = do_step(d, d < pr.L, tail, U1{}); else z = do_step(d, d < pr.L, tail, U0{});
-            if (z) { stop = AGATHA_STOP_ZDROP; d_stop = d + 1; done = true; break; }
-            if (WODD) z = do_step(d + 1, d + 1 < pr.L, tail, U0{}); else z = do_step(d + 1, d + 1 < pr.L, tail, U1{});
-            if (z) { stop = AGATHA_STOP_ZDROP; d_stop = d + 2; done = true; break; }
+    // first d whose valid k-range is clipped by the far matrix edges (q = qlen-1 or r = tcols-1)
+    const int d_tail = min(2 * pr.qlen - 2 - W, 2 * pr.tcols - 2 - W) + 1;
+    const int d_fast_lo = (W + 2) & ~1;                                   // even, > W: no injection, band edges are real
+    const int d_fast_hi = min(d_tail - 1, pr.L - 1) & ~1;                 // FAST pairs (d, d+1) need d+1 < d_tail and d+1 < L
+    int d = 0;
+    for (int i = 0;; i += p.sw) {
+        bool wrap = false;
+        int dend;
+        if (i >= pr.total) {
+            // job wrap-up, agatha_kernel.h:334-356: 8 more anti-diagonals are scanned (without the d < L guard) when the
+            // slice loop ended exactly on total_anti_diags; otherwise those ring slots are empty (see oracle).
+            if (i != pr.total) break;
+            wrap = true; dend = 8 * pr.total + 8;
+        } else {
+            // slice bounds, agatha_kernel.h:183-191 (truncating division as in the reference)
+            int ss = max(0, i - pr.pq + 1);
+            ss = max(ss, (i * 8 + 8 - W) / 2 / 8);
+            int se = min(pr.pt - 1, i + p.sw - 1);
+            se = min(se, ((i + p.sw - 1) * 8 + 7 + W) / 2 / 8);
+            if (ss > se) { stop = AGATHA_STOP_BANDEXIT; d_stop = min(8 * i, pr.L); break; }
+            dend = 8 * (i + p.sw);
         }
-    }
-    // job wrap-up, agatha_kernel.h:334-356: 8 more anti-diagonals are scanned (without the d < L guard) when the
-    // slice loop ended exactly on total_anti_diags; otherwise those ring slots are empty (see oracle).
-    if (!done && i == pr.total) {
-        const int dend = 8 * pr.total + 8;
-        for (; d < dend && !done; d += 2) {
-            bool z;
-            if (WODD) z = do_step(d, true, true, U1{}); else z = do_step(d, true, true, U0{});
-            if (z) { if (d < pr.L) { stop = AGATHA_STOP_ZDROP; d_stop = d + 1; } break; }
-            if (WODD) z = do_step(d + 1, true, true, U0{}); else z = do_step(d + 1, true, true, U1{});
-            if (z) { if (d + 1 < pr.L) { stop = AGATHA_STOP_ZDROP; d_stop = d + 2; } break; }
+        bool fired = false;
+        while (d < dend) {
+            if (d >= d_fast_lo && d < d_fast_hi) {
+                const int dlim = min(dend, d_fast_hi);
+#pragma unroll 1
+                for (; d < dlim; d += 2) {
+                    if (do_step(d, true, UA{}, std::true_type{})) { fired = true; break; }
+                    if (do_step(d + 1, true, UB{}, std::true_type{})) { fired = true; d++; break; }
+                }
+                if (fired) break;
+            } else {
+                if (do_step(d, wrap || d < pr.L, UA{}, std::false_type{})) { fired = true; break; }
+                if (do_step(d + 1, wrap || d + 1 < pr.L, UB{}, std::false_type{})) { fired = true; d++; break; }
+                d += 2;
+            }
         }
+        if (fired) { if (d < pr.L) { stop = AGATHA_STOP_ZDROP; d_stop = d + 1; } break; }
+        if (wrap) break;
     }
     out_score = st.max; out_qend = st.mq; out_tend = st.mt; out_stop = stop; out_dstop = d_stop;
 }
@@ -413,7 +425,7 @@ __device__ __noinline__ void run_pair(const Pair& pr, const KernelParams& p, int
 // Persistent kernel: every warp pulls alignments from a queue ordered longest-first by the host scheduler.
 // ---------------------------------------------------------------------------------------------------------------
 template <int C, bool WODD, int JWS>
-__global__ void __launch_bounds__(128, 3) extend_kernel(JobArrays ja, KernelParams p)
+__global__ void __launch_bounds__(128, (C <= 24 ? 3 : 2)) extend_kernel(JobArrays ja, KernelParams p)
 {
     const int lane = threadIdx.x & 31;
     for (;;) {

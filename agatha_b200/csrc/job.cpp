@@ -1,0 +1,200 @@
+// Whole-job API: any number of pairs over any number of GPUs of one box (agatha_align_job, include/agatha_b200.h).
+// The reference has no multi-GPU path (gasal_set_device exists, interfaces.cpp:86-116, but its only call is commented
+// out, test_prog.cpp:31). Pairs are independent, so there is no collective: a host scheduler balances estimated work
+// (cells inside the band) over the devices, one worker thread per device drives double-buffered streams, and results
+// are scattered back by original index.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "agatha_b200.h"
+#include "engine_internal.h"
+
+using namespace agatha;
+
+namespace {
+
+// Streams (pinned staging + device buffers) are expensive to create; keep them between jobs, per device.
+std::mutex g_pool_mu;
+std::map<int, std::vector<agatha_stream_t*>> g_pool;
+
+agatha_stream_t* pool_get(int device, uint32_t batch_alns)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto& v = g_pool[device];
+        if (!v.empty()) { agatha_stream_t* s = v.back(); v.pop_back(); return s; }
+    }
+    return agatha_stream_create(device, batch_alns, 1 << 20, 1 << 20);
+}
+
+void pool_put(int device, agatha_stream_t* s)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool[device].push_back(s);
+}
+
+struct Batch { agatha_stream_t* s = nullptr; std::vector<uint64_t> ids; bool busy = false; };
+
+struct Worker {
+    int device = 0;
+    std::vector<uint64_t> pairs;       // pair indices of this device, most expensive first
+    int rc = AGATHA_OK;
+    std::string err;
+    double kernel_ms = 0;
+    uint64_t h2d = 0, d2h = 0;
+    uint32_t batches = 0;
+};
+
+struct JobView {
+    const uint8_t *qb, *tb;
+    const uint64_t *qo, *to;
+    const uint32_t *ql, *tl;
+    const agatha_params_t* params;
+    int32_t *score, *qend, *tend, *stop, *dstop;
+};
+
+// Stage one batch exactly like gasal_host_batch_fill (host_batch.cpp:79-154): each sequence at a multiple of 8, padded with 'N'.
+int fill_batch(Batch& b, const JobView& jv, int fill_threads, uint64_t& qbytes, uint64_t& tbytes)
+{
+    const uint64_t n = b.ids.size();
+    const uint64_t qtot = agatha_staged_bytes(jv.ql, b.ids.data(), n), ttot = agatha_staged_bytes(jv.tl, b.ids.data(), n);
+    if (qtot > 0xfffffff8ull || ttot > 0xfffffff8ull) return set_error(AGATHA_EINVAL, "batch exceeds 4 GiB of bases; lower batch_alns");
+    int rc = agatha_stream_reserve(b.s, (uint32_t)n, qtot, ttot);
+    if (rc) return rc;
+    rc = agatha_stage_batch(jv.qb, jv.qo, jv.ql, b.ids.data(), n, agatha_stream_query_bases(b.s), qtot,
+                            agatha_stream_query_offsets(b.s), agatha_stream_query_lens(b.s), &qbytes, fill_threads);
+    if (rc) return rc;
+    return agatha_stage_batch(jv.tb, jv.to, jv.tl, b.ids.data(), n, agatha_stream_target_bases(b.s), ttot,
+                              agatha_stream_target_offsets(b.s), agatha_stream_target_lens(b.s), &tbytes, fill_threads);
+}
+
+void collect(Batch& b, const JobView& jv, Worker& w)
+{
+    const int32_t *sc = agatha_stream_scores(b.s), *qe = agatha_stream_query_ends(b.s), *te = agatha_stream_target_ends(b.s);
+    const int32_t *sp = agatha_stream_stops(b.s), *ds = agatha_stream_dstops(b.s);
+    for (size_t j = 0; j < b.ids.size(); j++) {
+        const uint64_t id = b.ids[j];
+        jv.score[id] = sc[j]; jv.qend[id] = qe[j]; jv.tend[id] = te[j];
+        if (jv.stop) jv.stop[id] = sp[j];
+        if (jv.dstop) jv.dstop[id] = ds[j];
+    }
+    float ms[3];
+    agatha_stream_timings(b.s, ms);
+    w.kernel_ms += ms[1];
+    w.d2h += 20ull * b.ids.size();
+    b.busy = false;
+}
+
+void run_worker(Worker& w, const JobView& jv, uint32_t batch_alns, int n_streams, int fill_threads)
+{
+    std::vector<Batch> bs((size_t)n_streams);
+    auto fail = [&](int rc) { w.rc = rc; w.err = agatha_last_error(); };
+    for (auto& b : bs) {
+        b.s = pool_get(w.device, batch_alns);
+        if (!b.s) { fail(AGATHA_ECUDA); break; }
+    }
+    size_t next = 0;
+    int cur = 0;
+    while (w.rc == AGATHA_OK && next < w.pairs.size()) {
+        Batch& b = bs[(size_t)cur];
+        if (b.busy) {                                  // oldest batch of this slot: wait for it, then reuse its buffers
+            int rc = agatha_stream_wait(b.s);
+            if (rc) { fail(rc); break; }
+            collect(b, jv, w);
+        }
+        const size_t cnt = std::min<size_t>(batch_alns, w.pairs.size() - next);
+        b.ids.assign(w.pairs.begin() + (long)next, w.pairs.begin() + (long)(next + cnt));
+        next += cnt;
+        uint64_t qbytes = 0, tbytes = 0;
+        int rc = fill_batch(b, jv, fill_threads, qbytes, tbytes);
+        if (!rc) rc = agatha_stream_submit(b.s, qbytes, tbytes, (uint32_t)cnt, jv.params);
+        if (rc) { fail(rc); break; }
+        b.busy = true;
+        w.h2d += qbytes + tbytes + 20ull * cnt;
+        w.batches++;
+        cur = (cur + 1) % n_streams;
+    }
+    for (auto& b : bs) {
+        if (b.s && b.busy) {
+            int rc = agatha_stream_wait(b.s);
+            if (rc && w.rc == AGATHA_OK) fail(rc);
+            if (!rc) collect(b, jv, w);
+        }
+        if (b.s) pool_put(w.device, b.s);
+    }
+}
+
+}  // namespace
+
+extern "C" void agatha_release_cached(void)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto& kv : g_pool) for (agatha_stream_t* s : kv.second) agatha_stream_destroy(s);
+    g_pool.clear();
+}
+
+extern "C" int agatha_align_job(const uint8_t* query_bases, const uint64_t* query_offsets, const uint32_t* query_lens,
+                                const uint8_t* target_bases, const uint64_t* target_offsets, const uint32_t* target_lens,
+                                uint64_t n_alns, const agatha_params_t* params, const agatha_job_config_t* cfg,
+                                int32_t* score, int32_t* query_end, int32_t* target_end, int32_t* stop, int32_t* dstop,
+                                agatha_job_stats_t* stats)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (!params || !score || !query_end || !target_end) return set_error(AGATHA_EINVAL, "NULL argument");
+    if (n_alns == 0) return AGATHA_OK;
+    if (!query_bases || !target_bases || !query_offsets || !target_offsets || !query_lens || !target_lens) return set_error(AGATHA_EINVAL, "NULL argument");
+    const int visible = agatha_device_count();
+    if (visible == 0) return set_error(AGATHA_ENODEV, "no CUDA device (agatha_b200 has no CPU fallback)");
+    int ndev = (cfg && cfg->n_devices > 0) ? cfg->n_devices : visible;
+    std::vector<int> devs((size_t)ndev);
+    for (int i = 0; i < ndev; i++) {
+        devs[(size_t)i] = (cfg && cfg->devices) ? cfg->devices[i] : i;
+        if (devs[(size_t)i] < 0 || devs[(size_t)i] >= visible) return set_error(AGATHA_EINVAL, "device %d not visible (%d devices)", devs[(size_t)i], visible);
+    }
+    const uint32_t batch_alns = (cfg && cfg->batch_alns) ? cfg->batch_alns : 16384u;
+    const int n_streams = (cfg && cfg->streams_per_device > 0) ? cfg->streams_per_device : 2;
+
+    // host scheduler: balance estimated cells over the devices, most expensive pairs first on every device
+    std::vector<int32_t> shard(n_alns);
+    int rc = agatha_shard_pairs(query_lens, target_lens, n_alns, params->band_width, ndev, shard.data());
+    if (rc) return rc;
+    std::vector<Worker> workers((size_t)ndev);
+    for (int i = 0; i < ndev; i++) workers[(size_t)i].device = devs[(size_t)i];
+    {
+        std::vector<uint64_t> idx(n_alns);
+        std::iota(idx.begin(), idx.end(), 0ull);
+        const int64_t W = params->band_width;
+        auto cost = [&](uint64_t i) { const uint64_t lo = std::min(query_lens[i], target_lens[i]), hi = std::max(query_lens[i], target_lens[i]); return lo * std::min<uint64_t>(2 * (uint64_t)std::max<int64_t>(W, 0) + 1, hi); };
+        std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return cost(a) > cost(b); });
+        for (uint64_t i : idx) workers[(size_t)shard[i]].pairs.push_back(i);
+    }
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int fill_threads = std::max(1, std::min(8, hw / ndev));
+    JobView jv{query_bases, target_bases, query_offsets, target_offsets, query_lens, target_lens, params, score, query_end, target_end, stop, dstop};
+    std::vector<std::thread> threads;
+    for (int i = 1; i < ndev; i++) threads.emplace_back(run_worker, std::ref(workers[(size_t)i]), std::cref(jv), batch_alns, n_streams, fill_threads);
+    run_worker(workers[0], jv, batch_alns, n_streams, fill_threads);
+    for (auto& t : threads) t.join();
+
+    double kmax = 0; uint64_t h2d = 0, d2h = 0; uint32_t nb = 0;
+    for (auto& w : workers) {
+        if (w.rc != AGATHA_OK) return set_error(w.rc, "device %d: %s", w.device, w.err.c_str());
+        kmax = std::max(kmax, w.kernel_ms); h2d += w.h2d; d2h += w.d2h; nb += w.batches;
+    }
+    if (stats) {
+        stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        stats->seconds_kernel_max = kmax * 1e-3;
+        stats->h2d_bytes = h2d; stats->d2h_bytes = d2h; stats->n_batches = nb; stats->n_devices = (uint32_t)ndev;
+    }
+    return AGATHA_OK;
+}

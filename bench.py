@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native guided-alignment engine.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                          (the reference arm: CPU, host cores)
+
+Workload (BASELINE.json configs[1]): 100,000 synthetic ONT-like read/reference pairs (~10 kb, ~10 % error), default
+AGAThA.sh scoring (-m 1 -x 4 -q 6 -r 2 -s 3 -z 400 -w 751). A "step" is one pass of the hot path (pack + banded
+extension with Z-drop) over the whole set. With N ranks every rank aligns its own 100,000 pairs (weak scaling, pairs are
+independent: no collective on the data path).
+
+  value  alignments/s, inputs resident in HBM (unpacked bases on the device), CUDA-event time, max over ranks
+  e2e    the same through the C ABI agatha_align_job() with HOST buffers: staging, H2D, pack, kernel, D2H in the timed region
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "alignments/s"
+WORKLOAD = "C2: 100k synthetic ONT-like pairs (~10 kb lognormal, 4/3/3 % sub/ins/del), -m 1 -x 4 -q 6 -r 2 -s 3 -z 400 -w 751"
+PROFILE, SEED = 2, 2
+OPS_PER_CELL = 10          # accounting constant, int32 ops per DP cell
+
+
+def load_int_peak():
+    """Measured B200 integer issue rate (profiles/int_peak_r01.json, agatha_b200/csrc/microbench/int_peak.cu):
+    the best mixed ALU+FMA-pipe stream. MEASURED_PEAKS.json only has HBM and bf16 numbers."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "int_peak_r01.json")) as f:
+            d = json.load(f)
+        best = max(v["tera_lane_ops_per_s"] for k, v in d.items() if isinstance(v, dict))
+        return best, "profiles/int_peak_r01.json (measured on this pool's B200: best mixed DPX/IMAD/PRMT stream)"
+    except Exception:
+        return 18.6, "fallback 148 SM x 64 lanes x 1.965 GHz (SURVEY 8d planning figure)"
+
+
+def load_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[1])); smax = max(smax, float(p[2]))
+                for nme, v in zip(names, p[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(oracle_mod, data, params, cores_hint=0, budget_s=15.0, use_ref_host=False):
+    """Time the CPU checker on a bounded, seeded sample of the same workload (all host threads)."""
+    n_total = len(data["qlen"])
+    orc = oracle_mod.Oracle()
+    ref = oracle_mod.RefHost() if (use_ref_host and oracle_mod.RefHost.available()) else None
+    p = oracle_mod.make_params(**params)
+    cores = os.cpu_count() or 1
+
+    def run(n):
+        idx = np.arange(n)
+        qoff = data["qoff"][idx].astype(np.uint64); toff = data["toff"][idx].astype(np.uint64)
+        # offsets of the first n pairs are already contiguous from 0
+        t0 = time.time()
+        if ref is not None:
+            ref.align_batch(data["qbuf"], qoff.astype(np.uint32), data["qlen"][:n], data["tbuf"], toff.astype(np.uint32), data["tlen"][:n], p, nthreads=0)
+        else:
+            orc.align_batch(data["qbuf"], qoff.astype(np.uint32), data["qlen"][:n], data["tbuf"], toff.astype(np.uint32), data["tlen"][:n], p, nthreads=0)
+        return time.time() - t0
+    probe_n = min(n_total, max(2 * cores, 8))
+    t_probe = run(probe_n)
+    n = int(min(n_total, max(probe_n, probe_n * budget_s / max(t_probe, 1e-3))))
+    n = max(cores, (n // cores) * cores)
+    t = run(n) if n != probe_n else t_probe
+    return {"value": n / t, "unit": METRIC, "cores": cores, "kind": "reference" if ref is not None else "port",
+            "sample": "first %d pairs of the workload, %.1f s, %s" % (n, t, "reference agatha_kernel.h compiled as host code (oracle/_ref), OpenMP over pairs"
+                                                                   if ref is not None else "scalar C oracle (oracle/agatha_oracle.c), OpenMP over pairs")}, n, t
+
+
+def run_reference_gpu(ag, data, params, n_pairs, tmpdir):
+    """Extra leg (not part of the contract lines): the UNMODIFIED reference GPU program built for sm_100
+    (oracle/_ref/agatha_ref_manual) on a slice of the same pairs, same box. Time = sum of raw.log (its own -p timing:
+    bucketing round trip + agatha_kernel per batch, gasal_align.cu:219-236)."""
+    from oracle import oracle_py as op
+    if not os.path.exists(op.REF_GPU_BIN):
+        return {"unavailable": "oracle/_ref/agatha_ref_manual not built"}
+    n = min(n_pairs, len(data["qlen"]))
+    qf, tf = os.path.join(tmpdir, "ref_q.fasta"), os.path.join(tmpdir, "ref_t.fasta")
+    ag.write_fasta(qf, data["qbuf"], data["qoff"], data["qlen"][:n])
+    ag.write_fasta(tf, data["tbuf"], data["toff"], data["tlen"][:n])
+    out = {}
+    flags = ["-m", str(params["match"]), "-x", str(params["mismatch"]), "-q", str(params["gap_open"]), "-r", str(params["gap_extend"]),
+             "-s", str(params["slice_width"]), "-z", str(params["z_threshold"]), "-w", str(params["band_width"])]
+    for name, extra in (("default_b256_t256_a8192", []), ("tuned_b296_t256_a8192", ["-b", "296", "-t", "256", "-a", "8192"])):
+        raw = os.path.join(tmpdir, "raw_%s.log" % name)
+        score = os.path.join(tmpdir, "score_%s.log" % name)
+        if os.path.exists(raw):
+            os.remove(raw)
+        t0 = time.time()
+        try:
+            with open(score, "w") as so:
+                r = subprocess.run([op.REF_GPU_BIN, "-p"] + flags + extra + [qf, tf, raw], stdout=so, stderr=subprocess.PIPE, text=True, timeout=600)
+            if r.returncode != 0:
+                out[name] = {"error": (r.stderr or "")[-300:]}
+                continue
+            ms = sum(float(x) for x in open(raw).read().split())
+            out[name] = {"pairs": n, "kernel_ms": ms, "alignments_per_s": n / (ms * 1e-3), "wall_s": time.time() - t0, "score_log": score}
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": repr(e)[:300]}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="agatha_b200", choices=["agatha_b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=100000, help="pairs per rank (default = the named config)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the extra reference-GPU-binary leg")
+    ap.add_argument("--ref-gpu-pairs", type=int, default=16384)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import agatha_b200 as ag
+    from agatha_b200._lib import DEFAULT_PARAMS
+    params = dict(DEFAULT_PARAMS)
+    W = params["band_width"]
+
+    # ------------------------------------------------------------------ reference arm: CPU, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import oracle_py as op
+        op.build(ref=False)
+        n_gen = min(args.pairs, 4096)
+        data = ag.synth_pairs(PROFILE, SEED, n_gen)
+        times, counts = [], []
+        info = None
+        for it in range(args.warmup + args.steps):
+            info, n, t = cpu_baseline(op, data, params, budget_s=min(args.cpu_budget, 12.0) if it >= args.warmup else 1.0, use_ref_host=True)
+            if it >= args.warmup:
+                times.append(t); counts.append(n)
+        value = sum(counts) / sum(times)
+        info["value"] = value
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU arm: the reference has no CPU implementation; its kernel header is compiled as host code (oracle/_ref) and run on all host threads on a bounded sample per step"},
+                "cpu_baseline": info, "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: agatha_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.pairs
+    data = ag.synth_pairs(PROFILE, SEED, n, first_pair=rank * n)
+    qlen, tlen = data["qlen"], data["tlen"]
+
+    # ---- device-resident leg: unpacked bases (reference host-batch layout) live in HBM before the timed region
+    sq, sqoff, _ = ag.stage_batch(data["qbuf"], data["qoff"], qlen, n_threads=8)
+    st_, stoff, _ = ag.stage_batch(data["tbuf"], data["toff"], tlen, n_threads=8)
+    order = ag.bucket_order(qlen, tlen, W)
+    d32 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+    tq = torch.from_numpy(sq).to(dev); tt = torch.from_numpy(st_).to(dev)
+    dqoff, dtoff, dqlen, dtlen, dorder = d32(sqoff), d32(stoff), d32(qlen), d32(tlen), d32(order)
+    p = ag.make_params(**params)
+    qp = torch.empty(tq.numel() // 8 + 64, dtype=torch.int32, device=dev)
+    tp = torch.empty(tt.numel() // 8 + 64, dtype=torch.int32, device=dev)
+    out = {k: torch.empty(n, dtype=torch.int32, device=dev) for k in ("score", "query_end", "target_end", "stop", "dstop")}
+    ws = torch.empty(256, dtype=torch.uint8, device=dev)
+    import ctypes
+    from agatha_b200._lib import check, lib
+    L = lib()
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def step(i=None):
+        check(L.agatha_pack_device(vp(tq), ctypes.c_uint64(tq.numel()), vp(tt), ctypes.c_uint64(tt.numel()), vp(qp), vp(tp), sp))
+        if i is not None:
+            ev_k0[i].record(stream)
+        check(L.agatha_extend_device(vp(qp), vp(tp), vp(dqoff), vp(dtoff), vp(dqlen), vp(dtlen), vp(dorder), ctypes.c_uint32(n), ctypes.byref(p),
+                                     vp(out["score"]), vp(out["query_end"]), vp(out["target_end"]), vp(out["stop"]), vp(out["dstop"]), vp(ws), sp))
+        if i is not None:
+            ev_k1[i].record(stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = ag.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    launches = ag.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = [a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)]
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    value = world * n / (ms_step * 1e-3)
+
+    # ---- cells actually needed (oracle's stop diagonal == kernel's dstop, parity-tested) -> GCUPS and the roofline
+    dstop = out["dstop"].cpu().numpy()
+    stops = out["stop"].cpu().numpy()
+    _, cells = ag.count_cells(qlen, tlen, W, dstop)
+    kms = statistics.mean(kernel_ms)
+    int_peak, int_src = load_int_peak()
+    hbm_peak, hbm_src = load_hbm_peak()
+    achieved = OPS_PER_CELL * cells / (kms * 1e-3) / 1e12
+    alg_bytes = int(((qlen.astype(np.int64) + 7) // 8 * 4 + (tlen.astype(np.int64) + 7) // 8 * 4 + 16 + 12).sum())
+    roofline = {"bound": "int_alu", "kernel": "agatha::extend_kernel<24,true,7>", "achieved": achieved, "peak": int_peak, "unit": "Tint-op/s", "frac": achieved / int_peak,
+                "peak_source": int_src, "ops_per_cell": OPS_PER_CELL, "cells_per_launch": cells, "kernel_ms": kms,
+                "gcups": cells / (kms * 1e-3) / 1e9, "traffic": None,
+                "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                        "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak},
+                "note": "integer-ALU bound by design (SURVEY 8d): ~1.4e3 cell updates per input byte; achieved = 10 int32 ops x needed cells / extension-kernel time"}
+
+    # ---- e2e leg: host buffers through the C ABI (staging memcpy + H2D + pack + kernel + D2H per step)
+    e2e_steps = max(1, min(args.steps, 3))
+    ag.align_job(data["qbuf"], data["qoff"], qlen, data["tbuf"], data["toff"], tlen, p, devices=[local_rank])   # warm-up (allocations)
+    barrier()
+    t0 = time.time()
+    h2d = d2h = 0
+    for _ in range(e2e_steps):
+        res, stats = ag.align_job(data["qbuf"], data["qoff"], qlen, data["tbuf"], data["toff"], tlen, p, devices=[local_rank])
+        h2d, d2h = stats["h2d_bytes"], stats["d2h_bytes"]
+    barrier()
+    t_e2e = (time.time() - t0) / e2e_steps
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n / float(te.item())
+    same = bool((res["score"] == out["score"].cpu().numpy()).all() and (res["query_end"] == out["query_end"].cpu().numpy()).all()
+                and (res["target_end"] == out["target_end"].cpu().numpy()).all())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline (rank 0, N = 1 only) and the reference GPU program, both outside every timed region
+    cpu = None
+    refgpu = None
+    if world == 1:
+        from oracle import oracle_py as op
+        try:
+            op.build(ref=False)
+            cpu, _, _ = cpu_baseline(op, data, params, budget_s=args.cpu_budget)
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": METRIC, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+        if not args.no_ref_gpu:
+            import tempfile
+            with tempfile.TemporaryDirectory() as td:
+                refgpu = run_reference_gpu(ag, data, params, args.ref_gpu_pairs, td)
+                # parity against the reference GPU kernel on the same pairs (informational; the tests gate it)
+                try:
+                    sc = np.loadtxt(refgpu["default_b256_t256_a8192"]["score_log"], dtype=str, delimiter="\t")
+                    ref_scores = sc[:, 0].astype(np.int64)
+                    ref_q = np.array([int(x.split("=")[1]) for x in sc[:, 1]]); ref_t = np.array([int(x.split("=")[1]) for x in sc[:, 2]])
+                    m = len(ref_scores)
+                    eq = (ref_scores == res["score"][:m]) & (ref_q == res["query_end"][:m]) & (ref_t == res["target_end"][:m])
+                    refgpu["parity_vs_ours"] = {"pairs": int(m), "identical": int(eq.sum())}
+                except Exception as e:  # noqa: BLE001
+                    refgpu["parity_vs_ours"] = {"error": repr(e)[:200]}
+                for v in refgpu.values():
+                    if isinstance(v, dict):
+                        v.pop("score_log", None)
+
+    line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": n, "l2": "inputs (%.2f GB unpacked + %.2f GB packed per GPU) exceed the 126 MB L2" % ((tq.numel() + tt.numel()) / 1e9, (tq.numel() + tt.numel()) / 2e9),
+                       "parallelism": "independent pairs sharded over %d GPU(s), no collective" % world,
+                       "stops": {"end": int((stops == 0).sum()), "zdrop": int((stops == 1).sum()), "bandexit": int((stops == 2).sum())}},
+            "gcups": world * cells / (ms_step * 1e-3) / 1e9,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "api": "agatha_align_job (C ABI, pageable host buffers -> pinned staging -> H2D -> pack -> extend -> D2H)", "matches_device_leg": same},
+            "gpu_launches": int(launches), "reference_gpu": refgpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -109,6 +109,8 @@ void agatha_stream_destroy(agatha_stream_t *s);
 /* Pinned staging the caller fills directly (like host_batch_t pages + host_*_offsets/lens, gasal.h:74-82,120-123).
  * agatha_stream_reserve grows them; pointers returned earlier are invalidated by a growing reserve. */
 int agatha_stream_reserve(agatha_stream_t *s, uint32_t n_alns, uint64_t query_bytes, uint64_t target_bytes);
+/* Current capacities of the pinned staging (any pointer may be NULL). */
+void agatha_stream_capacity(agatha_stream_t *s, uint32_t *max_alns, uint64_t *query_bytes, uint64_t *target_bytes);
 uint8_t *agatha_stream_query_bases(agatha_stream_t *s);
 uint8_t *agatha_stream_target_bases(agatha_stream_t *s);
 uint32_t *agatha_stream_query_offsets(agatha_stream_t *s);
@@ -158,6 +160,9 @@ int agatha_align_job(const uint8_t *query_bases, const uint64_t *query_offsets, 
                      int32_t *score, int32_t *query_end, int32_t *target_end, int32_t *stop, int32_t *dstop,
                      agatha_job_stats_t *stats);
 
+/* agatha_align_job keeps its streams (pinned staging, device buffers) for the next call; this frees them. */
+void agatha_release_cached(void);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Host utilities (no GPU needed).
  * ------------------------------------------------------------------------------------------------------------ */
@@ -175,6 +180,16 @@ int agatha_shard_pairs(const uint32_t *query_lens, const uint32_t *target_lens, 
  * dstop may be NULL (= whole matrix). */
 int agatha_count_cells(const uint32_t *query_lens, const uint32_t *target_lens, const int32_t *dstop, uint64_t n,
                        int32_t band_width, uint64_t *cells_out, uint64_t *total_out);
+
+/* Stage many sequences the way gasal_host_batch_fill does one (host_batch.cpp:79-154): sequence i is copied to the next
+ * multiple of 8 in dst and padded to a multiple of 8 with 'N'. dst_offsets (in bases == bytes) and *bytes_out follow the
+ * reference's conventions; dst may be pinned staging obtained from agatha_stream_*_bases(). Fails if the batch does not
+ * fit dst_capacity or 32-bit offsets. ids (optional) selects and orders the sequences: sequence j is ids[j]. */
+int agatha_stage_batch(const uint8_t *bases, const uint64_t *offsets, const uint32_t *lens, const uint64_t *ids, uint64_t n,
+                       uint8_t *dst, uint64_t dst_capacity, uint32_t *dst_offsets, uint32_t *dst_lens, uint64_t *bytes_out,
+                       int32_t n_threads);
+/* Bytes agatha_stage_batch will need. */
+uint64_t agatha_staged_bytes(const uint32_t *lens, const uint64_t *ids, uint64_t n);
 
 /* FASTA reader for the reference's input format: records ">>> idx" + sequence lines, both files read in
  * lock-step (test_prog.cpp:94-149). Returns an opaque handle or NULL. */

@@ -1,0 +1,57 @@
+"""Drop-in proof on the GPU box: the reference's own driver program, once linked with the reference library
+(oracle/_ref/agatha_ref_manual, built for sm_100) and once -- same unmodified test_prog.cpp -- linked with this
+repository's shim + libagatha_b200.so (oracle/_ref/agatha_dropin_manual), must print byte-identical score logs."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as op
+
+pytestmark = pytest.mark.gpu
+
+REF = op.REF_GPU_BIN
+DROPIN = os.path.join(os.path.dirname(op.REF_GPU_BIN), "agatha_dropin_manual")
+FLAGS = ["-m", "1", "-x", "4", "-q", "6", "-r", "2", "-s", "3", "-z", "400", "-w", "751"]   # AGAThA.sh:44
+
+
+def _run(binary, qf, tf, workdir, tag, extra=()):
+    raw = os.path.join(workdir, "raw_%s.log" % tag)
+    score = os.path.join(workdir, "score_%s.log" % tag)
+    with open(score, "w") as so:
+        r = subprocess.run([binary, "-p"] + FLAGS + list(extra) + [qf, tf, raw], stdout=so, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return open(score).read(), [float(x) for x in open(raw).read().split()]
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(DROPIN)), reason="oracle/_ref binaries not built (need /root/reference at build time)")
+def test_reference_driver_prints_identical_scores_with_either_library(tmp_path):
+    import agatha_b200 as ag
+    d = ag.synth_pairs(1, 1, 8192 + 700)           # C1 stand-in for the bundled dataset: two batches of the default 8192
+    qf, tf = str(tmp_path / "query.fasta"), str(tmp_path / "ref.fasta")
+    ag.write_fasta(qf, d["qbuf"], d["qoff"], d["qlen"])
+    ag.write_fasta(tf, d["tbuf"], d["toff"], d["tlen"])
+    ref_scores, ref_ms = _run(REF, qf, tf, str(tmp_path), "ref")
+    new_scores, new_ms = _run(DROPIN, qf, tf, str(tmp_path), "new")
+    assert len(ref_scores.splitlines()) == len(d["qlen"])
+    assert new_scores == ref_scores
+    assert len(new_ms) == len(ref_ms) == 2          # one raw.log line per batch, like the reference (gasal_align.cu:219-236)
+    # and the same through the C ABI job call
+    res, _ = ag.align_job(d["qbuf"], d["qoff"], d["qlen"], d["tbuf"], d["toff"], d["tlen"], ag.make_params())
+    lines = ["%d\tquery_batch_end=%d\ttarget_batch_end=%d" % (r["score"], r["query_end"], r["target_end"]) for r in res]
+    assert "\n".join(lines) + "\n" == ref_scores
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/agatha_ref_manual not built")
+def test_reference_gpu_kernel_agrees_on_long_ont_like_pairs(tmp_path):
+    import agatha_b200 as ag
+    d = ag.synth_pairs(2, 2, 3000)                  # C2 lengths, inside the reference's int16 domain
+    qf, tf = str(tmp_path / "q.fasta"), str(tmp_path / "t.fasta")
+    ag.write_fasta(qf, d["qbuf"], d["qoff"], d["qlen"])
+    ag.write_fasta(tf, d["tbuf"], d["toff"], d["tlen"])
+    ref_scores, _ = _run(REF, qf, tf, str(tmp_path), "ref")
+    res, _ = ag.align_job(d["qbuf"], d["qoff"], d["qlen"], d["tbuf"], d["toff"], d["tlen"], ag.make_params())
+    got = np.array([[r["score"], r["query_end"], r["target_end"]] for r in res])
+    exp = np.array([[int(a), int(b.split("=")[1]), int(c.split("=")[1])] for a, b, c in (ln.split("\t") for ln in ref_scores.splitlines())])
+    assert (got == exp).all()

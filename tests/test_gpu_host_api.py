@@ -1,0 +1,101 @@
+"""GPU tests of the host-level C ABI: whole-job call, stream protocol (the gasal_aln_async / gasal_is_aln_async_done
+equivalents), argument checks, growth, multi-batch double buffering -- all checked against the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as op
+from pairgen import make_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+def _exp(oracle, pairs, **pkw):
+    return oracle.align_pairs(pairs, op.make_params(**pkw))
+
+
+def _same(got, exp):
+    return all((got[a] == exp[b]).all() for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")))
+
+
+def test_align_job_many_small_batches(oracle):
+    import agatha_b200 as ag
+    pairs = make_pairs(31, 700, 5, 900, mixed=True)
+    got = ag.align_pairs(pairs, ag.make_params(band_width=63), batch_alns=64, streams_per_device=3)
+    assert _same(got, _exp(oracle, pairs, band_width=63))
+
+
+def test_align_job_synthetic_profiles_vs_oracle(oracle):
+    import agatha_b200 as ag
+    for prof, n, W in ((1, 400, 751), (2, 60, 751), (4, 300, 751)):
+        d = ag.synth_pairs(prof, prof, n)
+        res, stats = ag.align_job(d["qbuf"], d["qoff"], d["qlen"], d["tbuf"], d["toff"], d["tlen"], ag.make_params(band_width=W))
+        exp = oracle.align_batch(d["qbuf"], d["qoff"].astype(np.uint32), d["qlen"], d["tbuf"], d["toff"].astype(np.uint32), d["tlen"], op.make_params(band_width=W))
+        assert _same(res, exp), "profile %d" % prof
+        assert stats["h2d_bytes"] > 0 and stats["n_batches"] >= 1
+
+
+def test_full_size_properties_100k_pairs():
+    """BASELINE size (C2, 100k pairs): size-independent properties instead of the oracle -- idempotence, order invariance,
+    self-alignment of every target scores len*match and ends on the last base, coordinates inside the sequences."""
+    import agatha_b200 as ag
+    d = ag.synth_pairs(2, 2, 100000)
+    p = ag.make_params()
+    a, _ = ag.align_job(d["qbuf"], d["qoff"], d["qlen"], d["tbuf"], d["toff"], d["tlen"], p)
+    b, _ = ag.align_job(d["qbuf"], d["qoff"], d["qlen"], d["tbuf"], d["toff"], d["tlen"], p, batch_alns=5000)
+    assert (a == b).all()
+    assert (a["query_end"] < d["qlen"].astype(np.int64)).all() and (a["target_end"] < d["tlen"].astype(np.int64)).all()
+    assert (a["score"] > 0).all() and (a["score"] <= np.minimum(d["qlen"], d["tlen"])).all()
+    s, _ = ag.align_job(d["tbuf"], d["toff"], d["tlen"], d["tbuf"], d["toff"], d["tlen"], p)
+    assert (s["score"] == d["tlen"]).all() and (s["query_end"] == d["tlen"] - 1).all() and (s["target_end"] == d["tlen"] - 1).all()
+    assert (s["stop"] == 0).all()
+    # checksum of checksums: a permutation of the pairs permutes the results
+    perm = np.random.default_rng(0).permutation(20000)
+    sub = lambda k: np.concatenate([d[k + "buf"][int(d[k + "off"][i]):int(d[k + "off"][i]) + int(d[k + "len"][i])] for i in perm])
+    ql, tl = d["qlen"][perm], d["tlen"][perm]
+    qo = np.concatenate([[0], np.cumsum(ql[:-1], dtype=np.uint64)]).astype(np.uint64); to = np.concatenate([[0], np.cumsum(tl[:-1], dtype=np.uint64)]).astype(np.uint64)
+    c, _ = ag.align_job(sub("q"), qo, ql, sub("t"), to, tl, p)
+    assert (c == a[perm]).all()
+
+
+def test_stream_protocol_and_argument_checks(oracle):
+    import agatha_b200 as ag
+    pairs = make_pairs(77, 300, 20, 1200, mixed=True)
+    qbuf, qoff, qlen, tbuf, toff, tlen = ag.stage_pairs(pairs)
+    s = ag.Stream(device=0, max_alns=16, max_query_bytes=64, max_target_bytes=64)   # far too small: must grow
+    assert s.poll() == -2                                  # nothing submitted (gasal_align.cu:279)
+    s.fill(qbuf, qoff, qlen, tbuf, toff, tlen)
+    p = ag.make_params(band_width=127)
+    s.submit(p)
+    rc = s.poll()
+    assert rc in (-1, 0)
+    s.wait()
+    assert s.poll() == -2
+    got = s.results()
+    assert _same(got, _exp(oracle, pairs, band_width=127))
+    t = s.timings()
+    assert t["kernel_ms"] > 0 and t["total_ms"] >= t["kernel_ms"]
+    # the reference's argument checks (gasal_align.cu:33-53)
+    for kw, msg in ((dict(n=0), "actual_n_alns"), (dict(qbytes=0), "actual_query_batch_bytes"), (dict(tbytes=0), "actual_target_batch_bytes"),
+                    (dict(qbytes=12), "multiple of 8"), (dict(tbytes=20), "multiple of 8")):
+        with pytest.raises(ag.AgathaError, match=msg):
+            s.submit(p, **kw)
+    with pytest.raises(ag.AgathaError, match="band_width"):
+        s.submit(ag.make_params(band_width=5000))
+    # reuse after an error, second batch on the same stream
+    s.submit(ag.make_params(band_width=63))
+    s.wait()
+    assert _same(s.results(), _exp(oracle, pairs, band_width=63))
+    s.close()
+
+
+def test_two_streams_overlap(oracle):
+    import agatha_b200 as ag
+    A = make_pairs(5, 200, 100, 2500, mixed=True)
+    B = make_pairs(6, 200, 100, 2500, mixed=True)
+    sa, sb = ag.Stream(), ag.Stream()
+    sa.fill(*ag.stage_pairs(A)); sb.fill(*ag.stage_pairs(B))
+    p = ag.make_params()
+    sa.submit(p); sb.submit(p)
+    sb.wait(); sa.wait()
+    assert _same(sa.results(), _exp(oracle, A)) and _same(sb.results(), _exp(oracle, B))
+    sa.close(); sb.close()
