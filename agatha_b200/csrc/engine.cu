@@ -30,50 +30,57 @@ int cuda_error(cudaError_t e, const char* what)
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// cells per lane for a band width: one warp covers global cell indices g in [0, 32*C), the band needs g <= W
-static int cells_per_lane(int W)
+// Kernel shape for a band width: a group of NW warps covers global cell indices g in [0, 32*NW*C); the band needs g <= W.
+struct Shape { int C, NW; };
+static Shape shape_for(int W)
 {
-    if (W < 32 * 8) return 8;
-    if (W < 32 * 16) return 16;
-    if (W < 32 * 24) return 24;
-    if (W < 32 * 32) return 32;
-    return 0;
+    if (W < 32 * 8) return {8, 1};
+    if (W < 32 * 16) return {16, 1};
+    if (W < 32 * 24) return {24, 1};
+    if (W < 32 * 32) return {32, 1};
+    if (W < 2 * 32 * 32) return {32, 2};
+    if (W < 4 * 32 * 32) return {32, 4};
+    if (W < 8 * 32 * 32) return {32, 8};
+    return {0, 0};
 }
 
-template <int C, bool WODD, int JWS>
+template <int C, int NW, bool WODD, int JWS>
 static int launch_variant(const JobArrays& ja, const KernelParams& kp, cudaStream_t st)
 {
     static int blocks_per_sm = 0;
     static int sms = 0;
+    constexpr int threads = KernelShape<C, NW>::threads;
     if (!blocks_per_sm) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         int b = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, extend_kernel<C, WODD, JWS>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, extend_kernel<C, NW, WODD, JWS>, threads, 0);
         blocks_per_sm = b > 0 ? b : 1;
     }
-    // persistent warps: never more warps than jobs, otherwise fill every SM
-    long long want = ((long long)ja.n + 3) / 4;
+    // persistent groups: never more groups than jobs, otherwise fill every SM
+    const int groups_per_block = NW == 1 ? 4 : 1;
+    long long want = ((long long)ja.n + groups_per_block - 1) / groups_per_block;
     long long grid = (long long)sms * blocks_per_sm;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    extend_kernel<C, WODD, JWS><<<(unsigned)grid, 128, 0, st>>>(ja, kp);
+    extend_kernel<C, NW, WODD, JWS><<<(unsigned)grid, threads, 0, st>>>(ja, kp);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_error(e, "extend_kernel launch");
     return AGATHA_OK;
 }
 
-template <int C>
+template <int C, int NW>
 static int launch_c(const JobArrays& ja, const KernelParams& kp, cudaStream_t st)
 {
     const bool wodd = kp.W & 1;
     if (wodd) {
-        if (kp.JW == 7) return launch_variant<C, true, 7>(ja, kp, st);       // every W == 7 (mod 8) with C == 8; W=751 with C == 24
-        return launch_variant<C, true, -1>(ja, kp, st);
+        if constexpr (NW == 1) { if (kp.JW == 7) return launch_variant<C, NW, true, 7>(ja, kp, st); }    // every W == 7 (mod 8) with C == 8; W = 751 with C == 24
+        if constexpr (NW > 1) { if (kp.JW == 31) return launch_variant<C, NW, true, 31>(ja, kp, st); }   // W = 4095 with C == 32
+        return launch_variant<C, NW, true, -1>(ja, kp, st);
     }
-    return launch_variant<C, false, -1>(ja, kp, st);
+    return launch_variant<C, NW, false, -1>(ja, kp, st);
 }
 
 int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
@@ -81,7 +88,7 @@ int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
     if (!p) return set_error(AGATHA_EINVAL, "params is NULL");
     if (p->band_width < 0) return set_error(AGATHA_EINVAL, "band_width < 0");
     if (p->slice_width < 1) return set_error(AGATHA_EINVAL, "slice_width < 1");
-    const int C = cells_per_lane(p->band_width);
+    const int C = shape_for(p->band_width).C;
     if (!C) return set_error(AGATHA_EUNSUPPORTED, "band_width %d > %d not supported by this build", p->band_width, agatha_max_band_width());
     kp->match = p->match; kp->mismatch = p->mismatch;
     kp->goe = p->gap_open + p->gap_extend;          // gasal_align.cu:301
@@ -116,7 +123,7 @@ int agatha_device_count(void)
     return n;
 }
 
-int agatha_max_band_width(void) { return 32 * 32 - 1; }
+int agatha_max_band_width(void) { return 8 * 32 * 32 - 1; }
 
 uint64_t agatha_launch_count(void) { return g_launches.load(); }
 
@@ -165,11 +172,15 @@ int agatha_extend_device(const uint32_t* d_query_packed, const uint32_t* d_targe
     ja.score = d_score; ja.qend = d_query_end; ja.tend = d_target_end; ja.stop = d_stop; ja.dstop = d_dstop;
     ja.counter = (unsigned*)d_workspace;
     ja.n = (int)n_alns;
-    switch (cells_per_lane(kp.W)) {
-        case 8: return launch_c<8>(ja, kp, st);
-        case 16: return launch_c<16>(ja, kp, st);
-        case 24: return launch_c<24>(ja, kp, st);
-        case 32: return launch_c<32>(ja, kp, st);
+    const Shape sh = shape_for(kp.W);
+    switch (sh.C * 100 + sh.NW) {
+        case 801: return launch_c<8, 1>(ja, kp, st);
+        case 1601: return launch_c<16, 1>(ja, kp, st);
+        case 2401: return launch_c<24, 1>(ja, kp, st);
+        case 3201: return launch_c<32, 1>(ja, kp, st);
+        case 3202: return launch_c<32, 2>(ja, kp, st);
+        case 3204: return launch_c<32, 4>(ja, kp, st);
+        case 3208: return launch_c<32, 8>(ja, kp, st);
     }
     return set_error(AGATHA_EUNSUPPORTED, "no kernel for band_width %d", kp.W);
 }

@@ -194,23 +194,29 @@ __device__ __forceinline__ bool has_rare_symbols(const Pair& pr, int lane)
 
 struct ScanState { int max, mt, mq; };
 
-// Termination Condition & Score Update for one anti-diagonal (agatha_kernel.h:292-314), warp-uniform.
-// `best` is this lane's key from step_cells. Returns true when Z-drop fires.
-template <int C>
-__device__ __forceinline__ bool scan_diag(ScanState& st, int best, int d, int u, int lane, const KernelParams& p)
+// Shared memory of one multi-warp group (NW > 1): lane-edge hand-over between neighbouring warps and the per-warp
+// anti-diagonal maxima. One __syncthreads per anti-diagonal; every slot is written before and read after it, and is
+// not written again before the next barrier, so no double buffering is needed for the edges; the scan slots
+// alternate by anti-diagonal parity.
+template <int NW>
+struct GroupShared {
+    int edgeE[NW];          // E[C-1] of lane 31 of each warp (published after steps of parity 1)
+    int edgeF[NW];          // F[0]   of lane 0  of each warp (published after steps of parity 0)
+    int scan_h[2][NW];      // per-warp maximum H of the anti-diagonal
+    int scan_g[2][NW];      // global cell index (C*gl + j) of that maximum, ties -> largest
+    unsigned job;
+};
+
+// Termination Condition & Score Update for one anti-diagonal (agatha_kernel.h:292-314), uniform across the group.
+// (hmax, g) is the anti-diagonal maximum and the global cell index of its right-most occurrence. Returns true when
+// Z-drop fires.
+__device__ __forceinline__ bool scan_update(ScanState& st, int hmax, int g, int d, int u, const KernelParams& p)
 {
-    const int v = best >> 5;
-    int hmax = __reduce_max_sync(FULL, v);
-    const bool newmax = hmax > st.max;
-    if (!newmax && (p.Z < 0 || (p.ge >= 0 && st.max - hmax <= p.Z))) return false;   // cannot fire: l*ge >= 0
     int r;
     if (hmax < -32768) {                 // empty ring slot reads as INT_MIN -> (h,r) = (-32768, 0), :152,:296-299
         hmax = -32768; r = 0;
     } else {
-        const unsigned who = __ballot_sync(FULL, v == hmax);
-        const int src = 31 - __clz((int)who);                                        // ties -> largest target index
-        const int jb = __shfl_sync(FULL, best & 31, src);
-        const int k = -p.W + 2 * (C * src + jb) + u;
+        const int k = -p.W + 2 * g + u;
         r = (d + k) >> 1;
     }
     if (hmax > st.max) { st.max = hmax; st.mt = r; st.mq = d - r; return false; }
@@ -222,18 +228,59 @@ __device__ __forceinline__ bool scan_diag(ScanState& st, int best, int d, int u,
     return false;
 }
 
+// Single-warp group: `best` is this lane's key from step_cells.
+template <int C>
+__device__ __forceinline__ bool scan_diag(ScanState& st, int best, int d, int u, int lane, const KernelParams& p)
+{
+    const int v = best >> 5;
+    const int hmax = __reduce_max_sync(FULL, v);
+    if (hmax <= st.max && (p.Z < 0 || (p.ge >= 0 && st.max - hmax <= p.Z))) return false;   // cannot fire: l*ge >= 0
+    int g = 0;
+    if (hmax >= -32768) {
+        const unsigned who = __ballot_sync(FULL, v == hmax);
+        const int src = 31 - __clz((int)who);                                        // ties -> largest target index
+        g = C * src + __shfl_sync(FULL, best & 31, src);
+    }
+    return scan_update(st, hmax, g, d, u, p);
+}
+
+// Multi-warp group: publish this warp's maximum, meet the other warps, combine. Contains the group's only barrier of
+// the anti-diagonal, so it must be called by every warp on every step (scan == false just skips the update).
+template <int C, int NW>
+__device__ __forceinline__ bool scan_diag_group(ScanState& st, int best, int d, int u, int lane, int warp, bool scan,
+                                                GroupShared<NW>* sm, const KernelParams& p)
+{
+    const int v = best >> 5;
+    const int hw = __reduce_max_sync(FULL, v);
+    const unsigned who = __ballot_sync(FULL, v == hw);
+    const int src = 31 - __clz((int)who);
+    const int gw = C * (32 * warp + src) + __shfl_sync(FULL, best & 31, src);
+    if (lane == 0) { sm->scan_h[d & 1][warp] = hw; sm->scan_g[d & 1][warp] = gw; }
+    __syncthreads();
+    if (!scan) return false;
+    const int hv = lane < NW ? sm->scan_h[d & 1][lane] : INT_MIN;
+    const int hmax = __reduce_max_sync(FULL, hv);
+    if (hmax <= st.max && (p.Z < 0 || (p.ge >= 0 && st.max - hmax <= p.Z))) return false;
+    const unsigned whow = __ballot_sync(FULL, lane < NW && hv == hmax);
+    const int srcw = 31 - __clz((int)whow);                                          // ties -> largest target index
+    const int g = sm->scan_g[d & 1][srcw];
+    return scan_update(st, hmax, g, d, u, p);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// One alignment, one warp.  WODD = (W & 1): fixes which parity class the even anti-diagonals use.
+// One alignment, one group of NW warps (NW == 1: a single warp, no shared memory, no barrier).
+// WODD = (W & 1): fixes which parity class the even anti-diagonals use.
 // JWS >= 0: the cell index of k = +W inside its lane is known at compile time (W % C == JWS); -1: run-time.
 //
 // Two loop bodies only, so that the steady state stays small and branch-free:
 //   FAST  anti-diagonals W < d < d_tail: every lane's cells are inside the matrix, nothing to inject or mask
 //   SLOW  everything else: matrix-edge injection (d < W), far-edge masking, padding-column patch, wrap-up
 // ---------------------------------------------------------------------------------------------------------------
-template <int C, bool WODD, int JWS, bool GENERIC>
-__device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, int lane,
+template <int C, int NW, bool WODD, int JWS, bool GENERIC>
+__device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, int lane, int warp, GroupShared<NW>* sm,
                                          int& out_score, int& out_qend, int& out_tend, int& out_stop, int& out_dstop)
 {
+    const int gl = 32 * warp + lane;                 // lane index inside the group: owns cells g in [C*gl, C*gl + C)
     static_assert(C % 8 == 0 && C <= 32, "cells per lane must be a multiple of 8");
     constexpr int NWORD = C / 8;
     using U0 = std::integral_constant<int, 0>;
@@ -247,8 +294,8 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     for (int j = 0; j < C; j++) { H0[j] = NEGBIG; H1[j] = NEGBIG; E[j] = NEGBIG; F[j] = NEGBIG; }
 
     // --- sequence windows at d = 0: nibble j <-> query[qtop - j], target[rbot + j] ---------------------------
-    int qtop = (W >> 1) - C * lane;                 // ((d+W)>>1) - C*lane at d = 0
-    int rbot = ((1 - W) >> 1) + C * lane;           // ((d-W+1)>>1) + C*lane at d = 0
+    int qtop = (W >> 1) - C * gl;                   // ((d+W)>>1) - C*gl at d = 0
+    int rbot = ((1 - W) >> 1) + C * gl;             // ((d-W+1)>>1) + C*gl at d = 0
     uint32_t Qw[NWORD], Rw[NWORD];
 #pragma unroll
     for (int w = 0; w < NWORD; w++) { Qw[w] = 0u; Rw[w] = 0u; }
@@ -277,7 +324,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         {   // top: consumer (0, d+1) reads F; (0, d+2) reads H as its diagonal
             const int g = (d + 2 + W) >> 1;
             const int ln = g / C, j = g - ln * C;
-            if (lane == ln) {
+            if (gl == ln) {
                 if ((d + 2) <= W) { if (U == 0) poke<C>(H0, j, hv); else poke<C>(H1, j, hv); }
                 poke<C>(F, j, gv);
             }
@@ -285,7 +332,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         if (W - d - 2 >= 0) {   // left: consumer (d+1, 0) reads E; (d+2, 0) reads H as its diagonal
             const int g = (W - d - 2) >> 1;
             const int ln = g / C, j = g - ln * C;
-            if (lane == ln) {
+            if (gl == ln) {
                 if (U == 0) poke<C>(H0, j, hv); else poke<C>(H1, j, hv);
                 poke<C>(E, j, gv);
             }
@@ -294,14 +341,14 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     {
         const int g = W >> 1;                       // k = 0: 2g + u = W, u = W & 1
         const int ln = g / C, j = g - ln * C;
-        if (lane == ln) { if (WODD) poke<C>(H1, j, 0); else poke<C>(H0, j, 0); }
+        if (gl == ln) { if (WODD) poke<C>(H1, j, 0); else poke<C>(H0, j, 0); }
         inject(-1, UB{});                           // u(-1) = (W-1) & 1
     }
 
     ScanState st = {0, 0, 0};                        // agatha_kernel.h:158-161
     int stop = AGATHA_STOP_END, d_stop = pr.L;
     const bool has_phantom = pr.tcols > pr.tlen;
-    const bool edge_lane = (lane == p.LW);
+    const bool edge_lane = (gl == p.LW);
 
     // phantom (padding) target columns: their F and diagonal inputs restart from MINUS_INF2 at the first row of every
     // slice chunk of the last target block (agatha_kernel.h:206-221 reload, :272-279 never stored); see oracle.
@@ -315,10 +362,10 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         const int g = (k + W - U) >> 1;              // cell (g,U) itself
         const int gf = (U == 0) ? g : g + 1;         // its F input: U==0 reads F[j], U==1 reads F[j+1] / next lane's F[0]
         const int lnf = gf / C, jf = gf - lnf * C;
-        if (lane == lnf) poke<C>(F, jf, NEG16);
+        if (gl == lnf) poke<C>(F, jf, NEG16);
         if (r - 1 >= pr.tlen) {
             const int ln = g / C, j = g - ln * C;
-            if (lane == ln) { if (U == 0) poke<C>(H0, j, NEG16); else poke<C>(H1, j, NEG16); }
+            if (gl == ln) { if (U == 0) poke<C>(H0, j, NEG16); else poke<C>(H1, j, NEG16); }
         }
     };
 
@@ -345,43 +392,66 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     auto do_step = [&](int d, bool scan, auto u_tag, auto fast_tag) -> bool {
         constexpr int U = decltype(u_tag)::value;
         constexpr bool FAST = decltype(fast_tag)::value;
+        using UN = std::integral_constant<int, 1 - U>;
         int jlo = 0, jhi = C - 1;
         if (!FAST) {
             const int klo = max(-W, max(-d, d - 2 * (pr.qlen - 1)));
             const int khi = min(W, min(d, 2 * (pr.tcols - 1) - d));
-            const int k0 = -W + 2 * C * lane + U;
+            const int k0 = -W + 2 * C * gl + U;
             jlo = (klo - k0 + 1) >> 1;               // ceil((klo-k0)/2)
             jhi = (khi - k0) >> 1;
-            if (has_phantom) phantom_patch(d, u_tag);
         }
         int best;
         if (U == 0) {
             int ein = __shfl_up_sync(FULL, E[C - 1], 1);
-            // k = -W: left of it is outside the band (MINUS_INF2), except on the matrix edge where E(W,0) is a boundary
-            // value (agatha_kernel.h:130); before the band edge enters the matrix the cell is not real: keep it dead
-            if (lane == 0) ein = (FAST || d > W) ? NEG16 : ((d == W) ? (-(p.goe + p.ge * W) - p.goe) : NEGBIG);
+            if (lane == 0) {
+                // k = -W: left of it is outside the band (MINUS_INF2), except on the matrix edge where E(W,0) is a boundary
+                // value (agatha_kernel.h:130); before the band edge enters the matrix the cell is not real: keep it dead
+                if (NW == 1 || warp == 0) ein = (FAST || d > W) ? NEG16 : ((d == W) ? (-(p.goe + p.ge * W) - p.goe) : NEGBIG);
+                else ein = sm->edgeE[warp - 1];
+            }
             best = step_cells<C, 0, !FAST, GENERIC>(H0, E, F, Qw, Rw, ein, p, jlo, jhi);
             if (edge_lane) { if (JWS >= 0) E[JWS >= 0 ? JWS : 0] = NEGBIG; else poke<C>(E, p.JW, NEGBIG); }   // nothing may leak into k = W+1
             shift_ref();
         } else {
             int fin = __shfl_down_sync(FULL, F[0], 1);
-            if (lane == 31) fin = NEGBIG;
+            if (lane == 31) {
+                if (NW == 1 || warp == NW - 1) fin = NEGBIG;
+                else fin = sm->edgeF[warp + 1];
+            }
             best = step_cells<C, 1, !FAST, GENERIC>(H1, E, F, Qw, Rw, fin, p, jlo, jhi);
             // k = W reads MINUS_INF2 from outside the band (agatha_kernel.h:138); F(0,W) is injected below at d = W-1
             if (edge_lane) { const int v = (FAST || d + 1 > W) ? NEG16 : NEGBIG; if (JWS >= 0) F[JWS >= 0 ? JWS : 0] = v; else poke<C>(F, p.JW, v); }
             shift_query();
         }
-        if (!FAST) { if (d < W) inject(d, u_tag); }
-        if (!scan) return false;
-        return scan_diag<C>(st, best, d, U, lane, p);
+        if (!FAST) {
+            if (d < W) inject(d, u_tag);
+            if (has_phantom) phantom_patch(d + 1, UN{});     // inputs of the next anti-diagonal, before they are handed over
+        }
+        if (NW == 1) {
+            if (!scan) return false;
+            return scan_diag<C>(st, best, d, U, lane, p);
+        } else {
+            if (U == 1) { if (lane == 31) sm->edgeE[warp] = E[C - 1]; }
+            else        { if (lane == 0) sm->edgeF[warp] = F[0]; }
+            return scan_diag_group<C, NW>(st, best, d, U, lane, warp, scan, sm, p);
+        }
     };
 
     // --- the slice schedule of the reference (agatha_kernel.h:180-330), replayed per anti-diagonal ----------------
     // first d whose valid k-range is clipped by the far matrix edges (q = qlen-1 or r = tcols-1)
-    const int d_tail = min(2 * pr.qlen - 2 - W, 2 * pr.tcols - 2 - W) + 1;
+    // (tlen, not tcols: the padding columns need the SLOW body's patches)
+    const int d_tail = min(2 * pr.qlen - 2 - W, 2 * pr.tlen - 2 - W) + 1;
     const int d_fast_lo = (W + 2) & ~1;                                   // even, > W: no injection, band edges are real
     const int d_fast_hi = min(d_tail - 1, pr.L - 1) & ~1;                 // FAST pairs (d, d+1) need d+1 < d_tail and d+1 < L
     int d = 0;
+    if (has_phantom) phantom_patch(0, UA{});
+    if (NW > 1) {
+        // hand-over slots must describe THIS alignment's initial state before the first step reads them
+        if (lane == 31) sm->edgeE[warp] = E[C - 1];
+        if (lane == 0) sm->edgeF[warp] = F[0];
+        __syncthreads();
+    }
     for (int i = 0;; i += p.sw) {
         bool wrap = false;
         int dend;
@@ -410,6 +480,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 }
                 if (fired) break;
             } else {
+                if (has_phantom && d == d_fast_hi && d > 0) phantom_patch(d, UA{});   // first SLOW step after the FAST run
                 if (do_step(d, wrap || d < pr.L, UA{}, std::false_type{})) { fired = true; break; }
                 if (do_step(d + 1, wrap || d + 1 < pr.L, UB{}, std::false_type{})) { fired = true; d++; break; }
                 d += 2;
@@ -422,16 +493,33 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Persistent kernel: every warp pulls alignments from a queue ordered longest-first by the host scheduler.
+// Persistent kernel: every group of NW warps pulls alignments from a queue ordered longest-first by the host
+// scheduler. NW == 1: 4 independent warps per CTA. NW > 1: one group per CTA (wide bands).
 // ---------------------------------------------------------------------------------------------------------------
-template <int C, bool WODD, int JWS>
-__global__ void __launch_bounds__(128, (C <= 24 ? 3 : 2)) extend_kernel(JobArrays ja, KernelParams p)
+template <int C, int NW>
+struct KernelShape {
+    static constexpr int threads = NW == 1 ? 128 : 32 * NW;
+    static constexpr int min_blocks = NW == 1 ? (C <= 24 ? 3 : 2) : (32 * NW * (C <= 16 ? 128 : 255) <= 32768 ? 2 : 1);
+};
+
+template <int C, int NW, bool WODD, int JWS>
+__global__ void __launch_bounds__(KernelShape<C, NW>::threads, KernelShape<C, NW>::min_blocks) extend_kernel(JobArrays ja, KernelParams p)
 {
     const int lane = threadIdx.x & 31;
+    const int warp = NW == 1 ? 0 : (int)(threadIdx.x >> 5);
+    __shared__ GroupShared<(NW > 1 ? NW : 1)> smem;
+    GroupShared<NW>* sm = reinterpret_cast<GroupShared<NW>*>(&smem);
     for (;;) {
         unsigned job = 0;
-        if (lane == 0) job = atomicAdd(ja.counter, 1u);
-        job = __shfl_sync(FULL, job, 0);
+        if (NW == 1) {
+            if (lane == 0) job = atomicAdd(ja.counter, 1u);
+            job = __shfl_sync(FULL, job, 0);
+        } else {
+            __syncthreads();                          // everybody is done with the previous job's shared state
+            if (threadIdx.x == 0) sm->job = atomicAdd(ja.counter, 1u);
+            __syncthreads();
+            job = sm->job;
+        }
         if (job >= (unsigned)ja.n) break;
         const unsigned idx = ja.order ? __ldg(ja.order + job) : job;
 
@@ -448,10 +536,10 @@ __global__ void __launch_bounds__(128, (C <= 24 ? 3 : 2)) extend_kernel(JobArray
 
         int score = 0, qend = 0, tend = 0, stop = AGATHA_STOP_END, dstop = 0;
         if (pr.qlen > 0 && pr.tlen > 0) {
-            if (has_rare_symbols(pr, lane)) run_pair<C, WODD, JWS, true>(pr, p, lane, score, qend, tend, stop, dstop);
-            else run_pair<C, WODD, JWS, false>(pr, p, lane, score, qend, tend, stop, dstop);
+            if (has_rare_symbols(pr, lane)) run_pair<C, NW, WODD, JWS, true>(pr, p, lane, warp, sm, score, qend, tend, stop, dstop);
+            else run_pair<C, NW, WODD, JWS, false>(pr, p, lane, warp, sm, score, qend, tend, stop, dstop);
         }
-        if (lane == 0) {
+        if (lane == 0 && warp == 0) {
             ja.score[idx] = score; ja.qend[idx] = qend; ja.tend[idx] = tend;   // agatha_kernel.h:359-363
             if (ja.stop) ja.stop[idx] = stop;
             if (ja.dstop) ja.dstop[idx] = dstop;

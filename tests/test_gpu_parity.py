@@ -45,6 +45,24 @@ def test_random_pairs_vs_oracle(oracle, W, sw, Z, m, go):
     _cmp_oracle(oracle, pairs, dict(band_width=W, slice_width=sw, z_threshold=Z, match=m, gap_open=go), "random")
 
 
+@pytest.mark.parametrize("W,hi", [(1031, 3000), (2047, 5000), (2055, 5000), (4095, 7000), (4103, 9000), (8191, 9000)])
+def test_wide_bands_multi_warp_groups(oracle, W, hi):
+    # bands wider than one warp's registers: NW = 2, 4, 8 warps per alignment, one barrier per anti-diagonal
+    pairs = make_pairs(9700 + W, 40, 1, hi, mixed=True) + make_pairs(9800 + W, 6, hi, hi + 500, err=0.01)
+    _cmp_oracle(oracle, pairs, dict(band_width=W), "wide")
+    _cmp_oracle(oracle, pairs[:24], dict(band_width=W, z_threshold=60, slice_width=1), "wide z60")
+
+
+def test_hifi_like_wide_band_profile(oracle):
+    # C3: HiFi-like 15 kb pairs, -w 4095
+    import agatha_b200 as ag
+    d = ag.synth_pairs(3, 3, 24)
+    res, _ = ag.align_job(d["qbuf"], d["qoff"], d["qlen"], d["tbuf"], d["toff"], d["tlen"], ag.make_params(band_width=4095))
+    exp = oracle.align_batch(d["qbuf"], d["qoff"].astype(np.uint32), d["qlen"], d["tbuf"], d["toff"].astype(np.uint32), d["tlen"], op.make_params(band_width=4095))
+    for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
+        assert (res[a] == exp[b]).all(), a
+
+
 def test_even_and_odd_unaligned_band_widths(oracle):
     # strict band semantics for widths the reference does not define exactly: GPU == oracle
     for W in (0, 1, 8, 10, 33, 100, 750):
