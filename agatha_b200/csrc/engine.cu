@@ -100,6 +100,7 @@ int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
     const unsigned m = (unsigned)p->match & 0xffu, x = (unsigned)(-p->mismatch) & 0xffu;
     kp->tab_lo = m | (x << 8) | (x << 16) | (x << 24);
     kp->tab_hi = 0xffffffffu;
+    kp->one = 1; kp->k32 = 32;
     return AGATHA_OK;
 }
 

@@ -40,6 +40,7 @@ struct KernelParams {
     int match, mismatch, goe, ge, sw, Z, W;
     unsigned tab_lo, tab_hi;         // PRMT lookup table: byte x -> score for code XOR x (fast alphabet)
     int LW, JW;                      // lane / cell index of k = +W  (global cell index g = W, u = 0)
+    int one, k32;                    // the constants 1 and 32, opaque to ptxas: keep a*1+c and h*32+j on IMAD (FMA pipe)
 };
 
 struct JobArrays {
@@ -58,6 +59,15 @@ struct JobArrays {
     unsigned* counter;               // work queue head
     int n;
 };
+
+// Integer multiply-add that ptxas cannot strength-reduce to IADD3/LEA (b comes from the constant bank at run time).
+// ncu (profiles/extend_kernel_r01_ncu_full.csv): ALU pipe 81 % busy, FMA pipe 14 % -- every op moved here is free.
+__device__ __forceinline__ int imad(int a, int b, int c)
+{
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel)
 {
@@ -111,11 +121,11 @@ __device__ __forceinline__ int step_cells(int (&H)[C], int (&E)[C], int (&F)[C],
             m = H[j] + s;
         }
         const int h = __vimax3_s32(m, ein, fin);
-        const int t = m + mgoe;
+        const int t = imad(m, p.one, mgoe);
         E[j] = __viaddmax_s32(ein, mge, t);
         F[j] = __viaddmax_s32(fin, mge, t);
         H[j] = h;
-        int key = h * 32 + j;
+        int key = imad(h, p.k32, j);
         if (TAIL) key = (j >= jlo && j <= jhi) ? key : INT_MIN;
         if (jj & 1) best = __vimax3_s32(best, pend, key); else pend = key;
     }

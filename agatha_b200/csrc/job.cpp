@@ -102,6 +102,22 @@ void run_worker(Worker& w, const JobView& jv, uint32_t batch_alns, int n_streams
         b.s = pool_get(w.device, batch_alns);
         if (!b.s) { fail(AGATHA_ECUDA); break; }
     }
+    // size every stream for the largest batch of this job once, before the pipeline starts: no (re)allocation of pinned
+    // or device memory while batches are in flight, and none at all when the cached streams already fit
+    if (w.rc == AGATHA_OK) {
+        uint64_t qmax = 8, tmax = 8;
+        for (size_t at = 0; at < w.pairs.size(); at += batch_alns) {
+            const size_t cnt = std::min<size_t>(batch_alns, w.pairs.size() - at);
+            qmax = std::max(qmax, agatha_staged_bytes(jv.ql, w.pairs.data() + at, cnt));
+            tmax = std::max(tmax, agatha_staged_bytes(jv.tl, w.pairs.data() + at, cnt));
+        }
+        if (qmax > 0xfffffff8ull || tmax > 0xfffffff8ull) { set_error(AGATHA_EINVAL, "batch exceeds 4 GiB of bases; lower batch_alns"); fail(AGATHA_EINVAL); }
+        for (auto& b : bs) {
+            if (w.rc != AGATHA_OK) break;
+            int rc = agatha_stream_reserve(b.s, (uint32_t)std::min<size_t>(batch_alns, w.pairs.size()), qmax, tmax);
+            if (rc) fail(rc);
+        }
+    }
     size_t next = 0;
     int cur = 0;
     while (w.rc == AGATHA_OK && next < w.pairs.size()) {
@@ -129,8 +145,8 @@ void run_worker(Worker& w, const JobView& jv, uint32_t batch_alns, int n_streams
             if (rc && w.rc == AGATHA_OK) fail(rc);
             if (!rc) collect(b, jv, w);
         }
-        if (b.s) pool_put(w.device, b.s);
     }
+    for (auto it = bs.rbegin(); it != bs.rend(); ++it) if (it->s) pool_put(w.device, it->s);   // same stream, same slot next time
 }
 
 }  // namespace
@@ -161,8 +177,8 @@ extern "C" int agatha_align_job(const uint8_t* query_bases, const uint64_t* quer
         devs[(size_t)i] = (cfg && cfg->devices) ? cfg->devices[i] : i;
         if (devs[(size_t)i] < 0 || devs[(size_t)i] >= visible) return set_error(AGATHA_EINVAL, "device %d not visible (%d devices)", devs[(size_t)i], visible);
     }
-    const uint32_t batch_alns = (cfg && cfg->batch_alns) ? cfg->batch_alns : 16384u;
-    const int n_streams = (cfg && cfg->streams_per_device > 0) ? cfg->streams_per_device : 2;
+    const uint32_t batch_alns = (cfg && cfg->batch_alns) ? cfg->batch_alns : 8192u;   // the reference's kernel_align_num default (args_parser.cpp:23)
+    const int n_streams = (cfg && cfg->streams_per_device > 0) ? cfg->streams_per_device : 3;
 
     // host scheduler: balance estimated cells over the devices, most expensive pairs first on every device
     std::vector<int32_t> shard(n_alns);

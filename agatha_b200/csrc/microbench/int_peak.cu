@@ -13,7 +13,7 @@ constexpr int ILP = 8;
 constexpr int ITERS = 1 << 17;
 
 enum Op { OP_IADD, OP_IMAD, OP_LEA, OP_VIADDMAX, OP_VIMAX3, OP_VIADDMAX16, OP_VIMAX316, OP_DP4A, OP_PRMT, OP_LOP3, OP_SHF,
-          OP_MIX_ALU_FMA, OP_MIX_ALU2_FMA1, OP_MIX_CELL, OP_MIX_CELL_PRMT, OP_SHFL, OP_REDUX, OP_COUNT };
+          OP_MIX_ALU_FMA, OP_MIX_ALU2_FMA1, OP_MIX_CELL, OP_MIX_CELL_PRMT, OP_SHFL, OP_REDUX, OP_IMADHI, OP_IMADSHL, OP_MIX_CELL_HI, OP_COUNT };
 
 template <int OP>
 __global__ void __launch_bounds__(1024) bench(int* out, int a0, int b0, int c0, long long* clk)
@@ -70,6 +70,20 @@ __global__ void __launch_bounds__(1024) bench(int* out, int a0, int b0, int c0, 
                 int e = __viaddmax_s32(v[(i + 1) % ILP], b, t);
                 int f = __viaddmax_s32(v[(i + 2) % ILP], b, t);
                 int k = h * 32 + i;
+                v[i] = __vimax3_s32(e, f, k);
+                asm volatile("" : "+r"(v[i]));
+            }
+            else if (OP == OP_IMADHI) { asm volatile("mad.hi.s32 %0, %0, %1, %2;" : "+r"(v[i]) : "r"(b), "r"(c)); }
+            else if (OP == OP_IMADSHL) { asm volatile("mul.lo.s32 %0, %0, %1;" : "+r"(v[i]) : "r"(b)); }
+            else if (OP == OP_MIX_CELL_HI) {
+                // cell mix with mad.hi (FMA pipe) instead of dp4a: 1.75 FMA ops for the score add
+                int sh = v[i]; asm volatile("mul.lo.s32 %0, %0, %1;" : "+r"(sh) : "r"(b));
+                int m = v[(i + 3) % ILP]; asm volatile("mad.hi.s32 %0, %1, %2, %0;" : "+r"(m) : "r"(sh), "r"(c));
+                int t = m; asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(t) : "r"(b), "r"(c));
+                int h = __vimax3_s32(m, v[(i + 1) % ILP], v[(i + 2) % ILP]);
+                int e = __viaddmax_s32(v[(i + 1) % ILP], b, t);
+                int f = __viaddmax_s32(v[(i + 2) % ILP], b, t);
+                int k = h; asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(k) : "r"(c), "r"(b));
                 v[i] = __vimax3_s32(e, f, k);
                 asm volatile("" : "+r"(v[i]));
             }
@@ -140,7 +154,10 @@ int main()
     run<OP_MIX_CELL>("mix_cell7", 7, nsm, khz / 1e3, false);
     run<OP_MIX_CELL_PRMT>("mix_cell8_prmt", 8, nsm, khz / 1e3, false);
     run<OP_SHFL>("shfl", 1, nsm, khz / 1e3, false);
-    run<OP_REDUX>("redux_max", 1, nsm, khz / 1e3, true);
+    run<OP_REDUX>("redux_max", 1, nsm, khz / 1e3, false);
+    run<OP_IMADHI>("imad_hi", 1, nsm, khz / 1e3, false);
+    run<OP_IMADSHL>("imul_lo", 1, nsm, khz / 1e3, false);
+    run<OP_MIX_CELL_HI>("mix_cell8_madhi", 8, nsm, khz / 1e3, true);
     printf("}\n");
     return 0;
 }

@@ -86,47 +86,6 @@ void agatha_stream_destroy(agatha_stream_t* s)
     delete s;
 }
 
-// Grow-on-demand like the reference (host pages x2, host_batch.cpp:107-126; device buffers, gasal_align.cu:71-133).
-// Staged bytes/metadata already written are preserved.
-int agatha_stream_reserve(agatha_stream_t* s, uint32_t n_alns, uint64_t query_bytes, uint64_t target_bytes)
-{
-    if (!s) return set_error(AGATHA_EINVAL, "stream is NULL");
-    if (s->state == 1) return set_error(AGATHA_EINVAL, "reserve while a batch is in flight");
-    CK(cudaSetDevice(s->device), "cudaSetDevice");
-    int rc;
-    if ((rc = grow_host_bases(&s->h_q, &s->hcap_q, round_up(query_bytes, 8), s->hcap_q))) return rc;
-    if ((rc = grow_host_bases(&s->h_t, &s->hcap_t, round_up(target_bytes, 8), s->hcap_t))) return rc;
-    if (n_alns > s->cap_n) {
-        const uint32_t ncap = std::max<uint32_t>(n_alns, s->cap_n * 2);
-        uint32_t* nm = nullptr; int32_t* nr = nullptr;
-        CK(cudaHostAlloc((void**)&nm, sizeof(uint32_t) * 5ull * ncap, cudaHostAllocDefault), "cudaHostAlloc(meta)");
-        CK(cudaHostAlloc((void**)&nr, sizeof(int32_t) * 5ull * ncap, cudaHostAllocDefault), "cudaHostAlloc(results)");
-        if (s->h_meta) {
-            for (int k = 0; k < 5; k++) std::memcpy(nm + (size_t)k * ncap, s->h_meta + (size_t)k * s->cap_n, sizeof(uint32_t) * s->cap_n);
-            cudaFreeHost(s->h_meta);
-        }
-        if (s->h_res) {
-            for (int k = 0; k < 5; k++) std::memcpy(nr + (size_t)k * ncap, s->h_res + (size_t)k * s->cap_n, sizeof(int32_t) * s->cap_n);
-            cudaFreeHost(s->h_res);
-        }
-        s->h_meta = nm; s->h_res = nr; s->cap_n = ncap;
-    }
-    return AGATHA_OK;
-}
-
-void agatha_stream_capacity(agatha_stream_t* s, uint32_t* max_alns, uint64_t* query_bytes, uint64_t* target_bytes)
-{
-    if (max_alns) *max_alns = s->cap_n;
-    if (query_bytes) *query_bytes = s->hcap_q;
-    if (target_bytes) *target_bytes = s->hcap_t;
-}
-uint8_t* agatha_stream_query_bases(agatha_stream_t* s) { return s->h_q; }
-uint8_t* agatha_stream_target_bases(agatha_stream_t* s) { return s->h_t; }
-uint32_t* agatha_stream_query_offsets(agatha_stream_t* s) { return s->h_meta; }
-uint32_t* agatha_stream_target_offsets(agatha_stream_t* s) { return s->h_meta + (size_t)s->cap_n; }
-uint32_t* agatha_stream_query_lens(agatha_stream_t* s) { return s->h_meta + 2 * (size_t)s->cap_n; }
-uint32_t* agatha_stream_target_lens(agatha_stream_t* s) { return s->h_meta + 3 * (size_t)s->cap_n; }
-
 static int grow_device(agatha_stream_t* s, uint32_t n, uint64_t qbytes, uint64_t tbytes)
 {
     if (qbytes > s->dcap_q) {
@@ -152,6 +111,49 @@ static int grow_device(agatha_stream_t* s, uint32_t n, uint64_t qbytes, uint64_t
     }
     return AGATHA_OK;
 }
+
+// Grow-on-demand like the reference (host pages x2, host_batch.cpp:107-126; device buffers, gasal_align.cu:71-133).
+// Staged bytes/metadata already written are preserved.
+int agatha_stream_reserve(agatha_stream_t* s, uint32_t n_alns, uint64_t query_bytes, uint64_t target_bytes)
+{
+    if (!s) return set_error(AGATHA_EINVAL, "stream is NULL");
+    if (s->state == 1) return set_error(AGATHA_EINVAL, "reserve while a batch is in flight");
+    CK(cudaSetDevice(s->device), "cudaSetDevice");
+    int rc;
+    if ((rc = grow_host_bases(&s->h_q, &s->hcap_q, round_up(query_bytes, 8), s->hcap_q))) return rc;
+    if ((rc = grow_host_bases(&s->h_t, &s->hcap_t, round_up(target_bytes, 8), s->hcap_t))) return rc;
+    if (n_alns > s->cap_n) {
+        const uint32_t ncap = std::max<uint32_t>(n_alns, s->cap_n * 2);
+        uint32_t* nm = nullptr; int32_t* nr = nullptr;
+        CK(cudaHostAlloc((void**)&nm, sizeof(uint32_t) * 5ull * ncap, cudaHostAllocDefault), "cudaHostAlloc(meta)");
+        CK(cudaHostAlloc((void**)&nr, sizeof(int32_t) * 5ull * ncap, cudaHostAllocDefault), "cudaHostAlloc(results)");
+        if (s->h_meta) {
+            for (int k = 0; k < 5; k++) std::memcpy(nm + (size_t)k * ncap, s->h_meta + (size_t)k * s->cap_n, sizeof(uint32_t) * s->cap_n);
+            cudaFreeHost(s->h_meta);
+        }
+        if (s->h_res) {
+            for (int k = 0; k < 5; k++) std::memcpy(nr + (size_t)k * ncap, s->h_res + (size_t)k * s->cap_n, sizeof(int32_t) * s->cap_n);
+            cudaFreeHost(s->h_res);
+        }
+        s->h_meta = nm; s->h_res = nr; s->cap_n = ncap;
+    }
+    // device side too, so that a submit of anything that fits the reservation never allocates (cudaMalloc/cudaFree
+    // synchronise the whole device)
+    return grow_device(s, n_alns, round_up(query_bytes, 8), round_up(target_bytes, 8));
+}
+
+void agatha_stream_capacity(agatha_stream_t* s, uint32_t* max_alns, uint64_t* query_bytes, uint64_t* target_bytes)
+{
+    if (max_alns) *max_alns = s->cap_n;
+    if (query_bytes) *query_bytes = s->hcap_q;
+    if (target_bytes) *target_bytes = s->hcap_t;
+}
+uint8_t* agatha_stream_query_bases(agatha_stream_t* s) { return s->h_q; }
+uint8_t* agatha_stream_target_bases(agatha_stream_t* s) { return s->h_t; }
+uint32_t* agatha_stream_query_offsets(agatha_stream_t* s) { return s->h_meta; }
+uint32_t* agatha_stream_target_offsets(agatha_stream_t* s) { return s->h_meta + (size_t)s->cap_n; }
+uint32_t* agatha_stream_query_lens(agatha_stream_t* s) { return s->h_meta + 2 * (size_t)s->cap_n; }
+uint32_t* agatha_stream_target_lens(agatha_stream_t* s) { return s->h_meta + 3 * (size_t)s->cap_n; }
 
 int agatha_stream_submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns, const agatha_params_t* params)
 {

@@ -143,8 +143,8 @@ const int32_t *agatha_stream_dstops(agatha_stream_t *s);
 typedef struct {
     int32_t n_devices;        /* <= 0: use all visible devices */
     const int32_t *devices;   /* optional list of ordinals, NULL = 0..n_devices-1 */
-    uint32_t batch_alns;      /* alignments per batch, 0 = default */
-    int32_t streams_per_device; /* 0 = default (2) */
+    uint32_t batch_alns;      /* alignments per batch, 0 = default (8192) */
+    int32_t streams_per_device; /* 0 = default (3) */
 } agatha_job_config_t;
 
 typedef struct {

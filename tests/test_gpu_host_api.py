@@ -99,3 +99,23 @@ def test_two_streams_overlap(oracle):
     sb.wait(); sa.wait()
     assert _same(sa.results(), _exp(oracle, A)) and _same(sb.results(), _exp(oracle, B))
     sa.close(); sb.close()
+
+
+def test_job_sharded_over_all_visible_gpus(oracle):
+    """agatha_align_job over every GPU of the box (one worker thread + streams per device, LPT sharding, no collective):
+    same results as one device and as the oracle. Runs with one GPU too (then it only checks the device list path)."""
+    import agatha_b200 as ag
+    ndev = ag.device_count()
+    d = ag.synth_pairs(4, 11, 1500)                 # heavy tail + early Z-drop: uneven work, exercises the balancing
+    p = ag.make_params()
+    one, _ = ag.align_job(d["qbuf"], d["qoff"], d["qlen"], d["tbuf"], d["toff"], d["tlen"], p, devices=[0], batch_alns=256)
+    allg, stats = ag.align_job(d["qbuf"], d["qoff"], d["qlen"], d["tbuf"], d["toff"], d["tlen"], p, devices=list(range(ndev)), batch_alns=256)
+    assert (one == allg).all()
+    assert stats["n_devices"] == ndev
+    sub = np.arange(0, 1500, 7)
+    exp = oracle.align_pairs([(d["qbuf"][int(d["qoff"][i]):int(d["qoff"][i]) + int(d["qlen"][i])],
+                               d["tbuf"][int(d["toff"][i]):int(d["toff"][i]) + int(d["tlen"][i])]) for i in sub], op.make_params())
+    assert _same(allg[sub], exp)
+    if ndev > 1:
+        rev, _ = ag.align_job(d["qbuf"], d["qoff"], d["qlen"], d["tbuf"], d["toff"], d["tlen"], p, devices=list(range(ndev))[::-1])
+        assert (rev == one).all()
