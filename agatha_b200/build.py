@@ -17,7 +17,7 @@ LIB = os.path.join(LIBDIR, "libagatha_b200.so")
 STAMP = os.path.join(LIBDIR, "libagatha_b200.stamp")
 
 CUDA_SOURCES = ["engine.cu", "stream.cu"]
-CXX_SOURCES = ["host_utils.cpp", "fasta.cpp", "synth.cpp", "job.cpp", "gasal_compat.cpp"]
+CXX_SOURCES = ["host_utils.cpp", "fasta.cpp", "synth.cpp", "job.cpp", "gasal_compat.cpp"]   # manual_main.cpp is the driver, linked separately
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp,-Wall", "--default-stream", "per-thread"]
 
@@ -72,6 +72,14 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    # the command-line driver (reference contract: test_prog.cpp / args_parser.cpp), linked against the library
+    bindir = os.path.join(PKG, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(CSRC, "manual_main.cpp"), "-o", os.path.join(bindir, "agatha_manual"),
+           "-L" + LIBDIR, "-lagatha_b200", "-Wl,-rpath,$ORIGIN/../lib"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("driver link failed:\n" + r.stdout)
     with open(STAMP, "w") as f:
         f.write(dig)
     return LIB

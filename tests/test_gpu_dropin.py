@@ -55,3 +55,29 @@ def test_reference_gpu_kernel_agrees_on_long_ont_like_pairs(tmp_path):
     got = np.array([[r["score"], r["query_end"], r["target_end"]] for r in res])
     exp = np.array([[int(a), int(b.split("=")[1]), int(c.split("=")[1])] for a, b, c in (ln.split("\t") for ln in ref_scores.splitlines())])
     assert (got == exp).all()
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/agatha_ref_manual not built")
+def test_native_driver_and_runner_script_match_reference_outputs(tmp_path):
+    """agatha_manual (this repo's own driver, reference CLI contract) and tools/agatha.sh (AGAThA.sh-compatible runner:
+    raw.log, score.log, time.json) against the reference binary on the same FASTA files."""
+    import json
+    import agatha_b200 as ag
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    driver = os.path.join(root, "agatha_b200", "bin", "agatha_manual")
+    assert os.path.exists(driver), "run python -m agatha_b200.build"
+    d = ag.synth_pairs(1, 5, 3000)
+    ds = tmp_path / "dataset"; ds.mkdir()
+    # AGAThA.sh:44 passes ref.fasta first (query batch role) and query.fasta second (target batch role)
+    ag.write_fasta(str(ds / "ref.fasta"), d["qbuf"], d["qoff"], d["qlen"])
+    ag.write_fasta(str(ds / "query.fasta"), d["tbuf"], d["toff"], d["tlen"])
+    ref_scores, _ = _run(REF, str(ds / "ref.fasta"), str(ds / "query.fasta"), str(tmp_path), "ref")
+    new_scores, new_ms = _run(driver, str(ds / "ref.fasta"), str(ds / "query.fasta"), str(tmp_path), "drv")
+    assert new_scores == ref_scores and len(new_ms) == 1
+    out = tmp_path / "output"
+    r = subprocess.run(["bash", os.path.join(root, "tools", "agatha.sh"), "-i", "2", "-d", str(ds), "-o", str(out)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(out / "score.log").read() == ref_scores
+    assert len(open(out / "raw.log").read().split()) == 2
+    tj = json.load(open(out / "time.json"))
+    assert tj["AGAThA"]["test"] > 0

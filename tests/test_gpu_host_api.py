@@ -80,7 +80,7 @@ def test_stream_protocol_and_argument_checks(oracle):
         with pytest.raises(ag.AgathaError, match=msg):
             s.submit(p, **kw)
     with pytest.raises(ag.AgathaError, match="band_width"):
-        s.submit(ag.make_params(band_width=5000))
+        s.submit(ag.make_params(band_width=20000))
     # reuse after an error, second batch on the same stream
     s.submit(ag.make_params(band_width=63))
     s.wait()
