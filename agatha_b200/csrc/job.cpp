@@ -195,7 +195,7 @@ extern "C" int agatha_align_job(const uint8_t* query_bases, const uint64_t* quer
         for (uint64_t i : idx) workers[(size_t)shard[i]].pairs.push_back(i);
     }
     const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
-    const int fill_threads = std::max(1, std::min(8, hw / ndev));
+    const int fill_threads = (cfg && cfg->staging_threads > 0) ? cfg->staging_threads : std::max(1, std::min(8, hw / ndev));
     JobView jv{query_bases, target_bases, query_offsets, target_offsets, query_lens, target_lens, params, score, query_end, target_end, stop, dstop};
     std::vector<std::thread> threads;
     for (int i = 1; i < ndev; i++) threads.emplace_back(run_worker, std::ref(workers[(size_t)i]), std::cref(jv), batch_alns, n_streams, fill_threads);

@@ -19,7 +19,8 @@ def _ptr(a, ty):
 
 
 class JobConfig(ctypes.Structure):
-    _fields_ = [("n_devices", ctypes.c_int32), ("devices", i32p), ("batch_alns", ctypes.c_uint32), ("streams_per_device", ctypes.c_int32)]
+    _fields_ = [("n_devices", ctypes.c_int32), ("devices", i32p), ("batch_alns", ctypes.c_uint32), ("streams_per_device", ctypes.c_int32),
+                ("staging_threads", ctypes.c_int32)]
 
 
 class JobStats(ctypes.Structure):
@@ -115,7 +116,7 @@ def write_fasta(path, buf, off, lens):
             f.write(b"\n")
 
 
-def align_job(qbuf, qoff, qlen, tbuf, toff, tlen, params, devices=None, n_devices=0, batch_alns=0, streams_per_device=0):
+def align_job(qbuf, qoff, qlen, tbuf, toff, tlen, params, devices=None, n_devices=0, batch_alns=0, streams_per_device=0, staging_threads=0):
     """agatha_align_job: pairs (unpadded ASCII, byte offsets) -> structured results in input order, plus stats dict."""
     qbuf, tbuf = _a(qbuf, np.uint8), _a(tbuf, np.uint8)
     qoff, toff = _a(qoff, np.uint64), _a(toff, np.uint64)
@@ -129,7 +130,7 @@ def align_job(qbuf, qoff, qlen, tbuf, toff, tlen, params, devices=None, n_device
         cfg.n_devices = len(dev_arr); cfg.devices = _ptr(dev_arr, i32p)
     else:
         cfg.n_devices = n_devices
-    cfg.batch_alns = batch_alns; cfg.streams_per_device = streams_per_device
+    cfg.batch_alns = batch_alns; cfg.streams_per_device = streams_per_device; cfg.staging_threads = staging_threads
     res = {k: np.zeros(n, np.int32) for k in ("score", "query_end", "target_end", "stop", "dstop")}
     st = JobStats()
     check(lib().agatha_align_job(_ptr(qbuf, u8p), _ptr(qoff, u64p), _ptr(qlen, u32p), _ptr(tbuf, u8p), _ptr(toff, u64p), _ptr(tlen, u32p),

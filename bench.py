@@ -303,12 +303,14 @@ def main():
 
     # ---- e2e leg: host buffers through the C ABI (staging memcpy + H2D + pack + kernel + D2H per step)
     e2e_steps = max(1, min(args.steps, 3))
-    ag.align_job(data["qbuf"], data["qoff"], qlen, data["tbuf"], data["toff"], tlen, p, devices=[local_rank])   # warm-up (allocations)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    stg = max(1, min(8, (os.cpu_count() or 8) // max(1, local_world)))          # host staging threads of this rank
+    ag.align_job(data["qbuf"], data["qoff"], qlen, data["tbuf"], data["toff"], tlen, p, devices=[local_rank], staging_threads=stg)   # warm-up (allocations)
     barrier()
     t0 = time.time()
     h2d = d2h = 0
     for _ in range(e2e_steps):
-        res, stats = ag.align_job(data["qbuf"], data["qoff"], qlen, data["tbuf"], data["toff"], tlen, p, devices=[local_rank])
+        res, stats = ag.align_job(data["qbuf"], data["qoff"], qlen, data["tbuf"], data["toff"], tlen, p, devices=[local_rank], staging_threads=stg)
         h2d, d2h = stats["h2d_bytes"], stats["d2h_bytes"]
     barrier()
     t_e2e = (time.time() - t0) / e2e_steps

@@ -145,6 +145,7 @@ typedef struct {
     const int32_t *devices;   /* optional list of ordinals, NULL = 0..n_devices-1 */
     uint32_t batch_alns;      /* alignments per batch, 0 = default (8192) */
     int32_t streams_per_device; /* 0 = default (3) */
+    int32_t staging_threads;  /* host threads per device that copy sequences into pinned staging, 0 = min(8, cores / devices) */
 } agatha_job_config_t;
 
 typedef struct {
