@@ -4,7 +4,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "extend_kernel.cuh"
+#include "extend_launch.cuh"
 #include "pack_kernel.cuh"
 #include "engine_internal.h"
 
@@ -44,30 +44,14 @@ static Shape shape_for(int W)
     return {0, 0};
 }
 
-template <int C, int NW, bool WODD, int JWS>
-static int launch_variant(const JobArrays& ja, const KernelParams& kp, cudaStream_t st)
+// The index of the band-edge cell inside its lane, JW = W % C, is a template constant for every band width that is
+// 7 (mod 8) -- the only residue for which the reference's band is exact -- and a run-time value otherwise.
+template <int C, int NW, int JW>
+static int launch_static_jw(const JobArrays& ja, const KernelParams& kp, cudaStream_t st, bool& done)
 {
-    static int blocks_per_sm = 0;
-    static int sms = 0;
-    constexpr int threads = KernelShape<C, NW>::threads;
-    if (!blocks_per_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int b = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, extend_kernel<C, NW, WODD, JWS>, threads, 0);
-        blocks_per_sm = b > 0 ? b : 1;
+    if constexpr (JW < C) {
+        if (kp.JW == JW) { done = true; return launch_variant<C, NW, true, JW>(ja, kp, st); }
     }
-    // persistent groups: never more groups than jobs, otherwise fill every SM
-    const int groups_per_block = NW == 1 ? 4 : 1;
-    long long want = ((long long)ja.n + groups_per_block - 1) / groups_per_block;
-    long long grid = (long long)sms * blocks_per_sm;
-    if (want < grid) grid = want;
-    if (grid < 1) grid = 1;
-    extend_kernel<C, NW, WODD, JWS><<<(unsigned)grid, threads, 0, st>>>(ja, kp);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_error(e, "extend_kernel launch");
     return AGATHA_OK;
 }
 
@@ -76,8 +60,11 @@ static int launch_c(const JobArrays& ja, const KernelParams& kp, cudaStream_t st
 {
     const bool wodd = kp.W & 1;
     if (wodd) {
-        if constexpr (NW == 1) { if (kp.JW == 7) return launch_variant<C, NW, true, 7>(ja, kp, st); }    // every W == 7 (mod 8) with C == 8; W = 751 with C == 24
-        if constexpr (NW > 1) { if (kp.JW == 31) return launch_variant<C, NW, true, 31>(ja, kp, st); }   // W = 4095 with C == 32
+        bool done = false;
+        int rc = launch_static_jw<C, NW, 7>(ja, kp, st, done);   if (done) return rc;
+        rc = launch_static_jw<C, NW, 15>(ja, kp, st, done);      if (done) return rc;
+        rc = launch_static_jw<C, NW, 23>(ja, kp, st, done);      if (done) return rc;
+        rc = launch_static_jw<C, NW, 31>(ja, kp, st, done);      if (done) return rc;
         return launch_variant<C, NW, true, -1>(ja, kp, st);
     }
     return launch_variant<C, NW, false, -1>(ja, kp, st);
@@ -154,6 +141,7 @@ int agatha_extend_device(const uint32_t* d_query_packed, const uint32_t* d_targe
                          int32_t* d_stop, int32_t* d_dstop, void* d_workspace, void* stream)
 {
     if (n_alns == 0) return set_error(AGATHA_EINVAL, "n_alns == 0");
+    if (n_alns > 0x7fffffffu) return set_error(AGATHA_EINVAL, "n_alns too large");
     if (!d_query_packed || !d_target_packed || !d_query_offsets || !d_target_offsets || !d_query_lens || !d_target_lens ||
         !d_score || !d_query_end || !d_target_end || !d_workspace)
         return set_error(AGATHA_EINVAL, "NULL device pointer");

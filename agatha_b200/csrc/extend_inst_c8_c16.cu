@@ -1,0 +1,13 @@
+// Explicit instantiations of the extension kernel (see extend_launch.cuh); one file per shape group for parallel builds.
+#define AGATHA_DEFINE_LAUNCH
+#include "extend_launch.cuh"
+
+namespace agatha {
+AGATHA_INSTANTIATE(8, 1, false, -1)
+AGATHA_INSTANTIATE(8, 1, true, -1)
+AGATHA_INSTANTIATE(8, 1, true, 7)
+AGATHA_INSTANTIATE(16, 1, false, -1)
+AGATHA_INSTANTIATE(16, 1, true, -1)
+AGATHA_INSTANTIATE(16, 1, true, 7)
+AGATHA_INSTANTIATE(16, 1, true, 15)
+}  // namespace agatha

@@ -133,24 +133,20 @@ __device__ __forceinline__ int step_cells(int (&H)[C], int (&E)[C], int (&F)[C],
     return best;
 }
 
-// Write `val` to arr[idx] with a run-time idx while keeping arr in registers: every case is a static index, and the
-// switch compiles to a jump, so the single lane that executes it pays a few instructions instead of C predicated moves.
+// Write `val` to arr[idx] with a run-time idx while keeping arr in registers: a compare + select per element (every index
+// is static). idx < 0 writes nothing, so a lane that does not own the target cell passes -1 and no branch is needed.
+// (A switch looks cheaper but ptxas materialises a copy of the whole array per case: ~120 moves per poke, measured.)
 template <int C>
 __device__ __forceinline__ void poke(int (&arr)[C], int idx, int val)
 {
-#define AGATHA_POKE_CASE(J) case J: if (J < C) arr[(J) < C ? (J) : 0] = val; break;
-    switch (idx) {
-        AGATHA_POKE_CASE(0)  AGATHA_POKE_CASE(1)  AGATHA_POKE_CASE(2)  AGATHA_POKE_CASE(3)
-        AGATHA_POKE_CASE(4)  AGATHA_POKE_CASE(5)  AGATHA_POKE_CASE(6)  AGATHA_POKE_CASE(7)
-        AGATHA_POKE_CASE(8)  AGATHA_POKE_CASE(9)  AGATHA_POKE_CASE(10) AGATHA_POKE_CASE(11)
-        AGATHA_POKE_CASE(12) AGATHA_POKE_CASE(13) AGATHA_POKE_CASE(14) AGATHA_POKE_CASE(15)
-        AGATHA_POKE_CASE(16) AGATHA_POKE_CASE(17) AGATHA_POKE_CASE(18) AGATHA_POKE_CASE(19)
-        AGATHA_POKE_CASE(20) AGATHA_POKE_CASE(21) AGATHA_POKE_CASE(22) AGATHA_POKE_CASE(23)
-        AGATHA_POKE_CASE(24) AGATHA_POKE_CASE(25) AGATHA_POKE_CASE(26) AGATHA_POKE_CASE(27)
-        AGATHA_POKE_CASE(28) AGATHA_POKE_CASE(29) AGATHA_POKE_CASE(30) AGATHA_POKE_CASE(31)
-        default: break;
-    }
-#undef AGATHA_POKE_CASE
+#pragma unroll
+    for (int j = 0; j < C; j++) arr[j] = (j == idx) ? val : arr[j];
+}
+template <int C>
+__device__ __forceinline__ void poke2(int (&a)[C], int va, int (&b)[C], int vb, int idx)
+{
+#pragma unroll
+    for (int j = 0; j < C; j++) { const bool hit = (j == idx); a[j] = hit ? va : a[j]; b[j] = hit ? vb : b[j]; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -333,25 +329,23 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         const int hv = -(p.goe + p.ge * jv), gv = hv - p.goe;
         {   // top: consumer (0, d+1) reads F; (0, d+2) reads H as its diagonal
             const int g = (d + 2 + W) >> 1;
-            const int ln = g / C, j = g - ln * C;
-            if (gl == ln) {
-                if ((d + 2) <= W) { if (U == 0) poke<C>(H0, j, hv); else poke<C>(H1, j, hv); }
-                poke<C>(F, j, gv);
-            }
+            const int j = g - C * gl;                                   // in [0,C) only in the owning lane
+            const int jj = (j >= 0 && j < C) ? j : -1;
+            if ((d + 2) <= W) { if (U == 0) poke2<C>(H0, hv, F, gv, jj); else poke2<C>(H1, hv, F, gv, jj); }
+            else poke<C>(F, jj, gv);
         }
         if (W - d - 2 >= 0) {   // left: consumer (d+1, 0) reads E; (d+2, 0) reads H as its diagonal
             const int g = (W - d - 2) >> 1;
-            const int ln = g / C, j = g - ln * C;
-            if (gl == ln) {
-                if (U == 0) poke<C>(H0, j, hv); else poke<C>(H1, j, hv);
-                poke<C>(E, j, gv);
-            }
+            const int j = g - C * gl;
+            const int jj = (j >= 0 && j < C) ? j : -1;
+            if (U == 0) poke2<C>(H0, hv, E, gv, jj); else poke2<C>(H1, hv, E, gv, jj);
         }
     };
     {
         const int g = W >> 1;                       // k = 0: 2g + u = W, u = W & 1
-        const int ln = g / C, j = g - ln * C;
-        if (gl == ln) { if (WODD) poke<C>(H1, j, 0); else poke<C>(H0, j, 0); }
+        const int j = g - C * gl;
+        const int jj = (j >= 0 && j < C) ? j : -1;
+        if (WODD) poke<C>(H1, jj, 0); else poke<C>(H0, jj, 0);
         inject(-1, UB{});                           // u(-1) = (W-1) & 1
     }
 
@@ -359,6 +353,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     int stop = AGATHA_STOP_END, d_stop = pr.L;
     const bool has_phantom = pr.tcols > pr.tlen;
     const bool edge_lane = (gl == p.LW);
+    const int jw_dyn = edge_lane ? p.JW : -1;
 
     // phantom (padding) target columns: their F and diagonal inputs restart from MINUS_INF2 at the first row of every
     // slice chunk of the last target block (agatha_kernel.h:206-221 reload, :272-279 never stored); see oracle.
@@ -371,11 +366,12 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         if (k > W || k < -W) return;
         const int g = (k + W - U) >> 1;              // cell (g,U) itself
         const int gf = (U == 0) ? g : g + 1;         // its F input: U==0 reads F[j], U==1 reads F[j+1] / next lane's F[0]
-        const int lnf = gf / C, jf = gf - lnf * C;
-        if (gl == lnf) poke<C>(F, jf, NEG16);
+        const int jf = gf - C * gl;
+        poke<C>(F, (jf >= 0 && jf < C) ? jf : -1, NEG16);
         if (r - 1 >= pr.tlen) {
-            const int ln = g / C, j = g - ln * C;
-            if (gl == ln) { if (U == 0) poke<C>(H0, j, NEG16); else poke<C>(H1, j, NEG16); }
+            const int j = g - C * gl;
+            const int jj = (j >= 0 && j < C) ? j : -1;
+            if (U == 0) poke<C>(H0, jj, NEG16); else poke<C>(H1, jj, NEG16);
         }
     };
 
@@ -421,7 +417,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 else ein = sm->edgeE[warp - 1];
             }
             best = step_cells<C, 0, !FAST, GENERIC>(H0, E, F, Qw, Rw, ein, p, jlo, jhi);
-            if (edge_lane) { if (JWS >= 0) E[JWS >= 0 ? JWS : 0] = NEGBIG; else poke<C>(E, p.JW, NEGBIG); }   // nothing may leak into k = W+1
+            if (JWS >= 0) { if (edge_lane) E[JWS >= 0 ? JWS : 0] = NEGBIG; } else poke<C>(E, jw_dyn, NEGBIG);   // nothing may leak into k = W+1
             shift_ref();
         } else {
             int fin = __shfl_down_sync(FULL, F[0], 1);
@@ -431,7 +427,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             }
             best = step_cells<C, 1, !FAST, GENERIC>(H1, E, F, Qw, Rw, fin, p, jlo, jhi);
             // k = W reads MINUS_INF2 from outside the band (agatha_kernel.h:138); F(0,W) is injected below at d = W-1
-            if (edge_lane) { const int v = (FAST || d + 1 > W) ? NEG16 : NEGBIG; if (JWS >= 0) F[JWS >= 0 ? JWS : 0] = v; else poke<C>(F, p.JW, v); }
+            { const int v = (FAST || d + 1 > W) ? NEG16 : NEGBIG; if (JWS >= 0) { if (edge_lane) F[JWS >= 0 ? JWS : 0] = v; } else poke<C>(F, jw_dyn, v); }
             shift_query();
         }
         if (!FAST) {

@@ -216,7 +216,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # pairs are independent: there is no GPU collective on this path. gloo carries the barrier and the max-over-ranks
+        # of the device-measured times (and keeps NCCL's banner off stdout, which must hold exactly one JSON line).
+        dist.init_process_group("gloo")
 
     n = args.pairs
     data = ag.synth_pairs(PROFILE, SEED, n, first_pair=rank * n)
@@ -279,7 +281,7 @@ def main():
     kernel_ms = [a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)]
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([ms_total], dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_step = float(tmax.item()) / args.steps
@@ -314,7 +316,7 @@ def main():
         h2d, d2h = stats["h2d_bytes"], stats["d2h_bytes"]
     barrier()
     t_e2e = (time.time() - t0) / e2e_steps
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    te = torch.tensor([t_e2e], dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n / float(te.item())
@@ -364,7 +366,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "api": "agatha_align_job (C ABI, pageable host buffers -> pinned staging -> H2D -> pack -> extend -> D2H)", "matches_device_leg": same},
             "gpu_launches": int(launches), "reference_gpu": refgpu}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
