@@ -505,7 +505,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
 template <int C, int NW>
 struct KernelShape {
     static constexpr int threads = NW == 1 ? 128 : 32 * NW;
-    static constexpr int min_blocks = NW == 1 ? (C <= 24 ? 3 : 2) : (32 * NW * (C <= 16 ? 128 : 255) <= 32768 ? 2 : 1);
+    static constexpr int min_blocks = NW == 1 ? (C <= 24 ? 3 : 2) : (32 * NW * (C <= 16 ? 128 : (C <= 24 ? 168 : 255)) <= 32768 ? 2 : 1);
 };
 
 template <int C, int NW, bool WODD, int JWS>
