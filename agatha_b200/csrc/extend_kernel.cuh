@@ -198,7 +198,15 @@ __device__ __forceinline__ bool has_rare_symbols(const Pair& pr, int lane)
     return __any_sync(FULL, rare);
 }
 
-struct ScanState { int max, mt, mq; };
+// thr: an anti-diagonal whose maximum is in [thr, max] can neither raise the maximum nor fire Z-drop (l*ge >= 0)
+struct ScanState { int max, mt, mq, thr; };
+
+__device__ __forceinline__ int scan_threshold(int mx, const KernelParams& p)
+{
+    if (p.ge < 0) return INT_MAX;            // no shortcut: the l*ge term could lower the bar
+    if (p.Z < 0) return INT_MIN;             // Z-drop disabled
+    return mx - p.Z;
+}
 
 // Shared memory of one multi-warp group (NW > 1): lane-edge hand-over between neighbouring warps and the per-warp
 // anti-diagonal maxima. One __syncthreads per anti-diagonal; every slot is written before and read after it, and is
@@ -225,7 +233,7 @@ __device__ __forceinline__ bool scan_update(ScanState& st, int hmax, int g, int 
         const int k = -p.W + 2 * g + u;
         r = (d + k) >> 1;
     }
-    if (hmax > st.max) { st.max = hmax; st.mt = r; st.mq = d - r; return false; }
+    if (hmax > st.max) { st.max = hmax; st.mt = r; st.mq = d - r; st.thr = scan_threshold(hmax, p); return false; }
     if (r >= st.mt && d - r >= st.mq) {
         const int tl = r - st.mt, ql = (d - r) - st.mq;
         const int l = tl > ql ? tl - ql : ql - tl;
@@ -234,16 +242,15 @@ __device__ __forceinline__ bool scan_update(ScanState& st, int hmax, int g, int 
     return false;
 }
 
-// Single-warp group: `best` is this lane's key from step_cells.
+// Single-warp group: `best` is this lane's key from step_cells (H*32 + j).
 template <int C>
 __device__ __forceinline__ bool scan_diag(ScanState& st, int best, int d, int u, int lane, const KernelParams& p)
 {
-    const int v = best >> 5;
-    const int hmax = __reduce_max_sync(FULL, v);
-    if (hmax <= st.max && (p.Z < 0 || (p.ge >= 0 && st.max - hmax <= p.Z))) return false;   // cannot fire: l*ge >= 0
+    const int hmax = __reduce_max_sync(FULL, best) >> 5;          // H dominates the key, so this is the maximum H
+    if (hmax <= st.max && hmax >= st.thr) return false;           // common case: nothing can happen on this anti-diagonal
     int g = 0;
     if (hmax >= -32768) {
-        const unsigned who = __ballot_sync(FULL, v == hmax);
+        const unsigned who = __ballot_sync(FULL, (best >> 5) == hmax);
         const int src = 31 - __clz((int)who);                                        // ties -> largest target index
         g = C * src + __shfl_sync(FULL, best & 31, src);
     }
@@ -266,7 +273,7 @@ __device__ __forceinline__ bool scan_diag_group(ScanState& st, int best, int d, 
     if (!scan) return false;
     const int hv = lane < NW ? sm->scan_h[d & 1][lane] : INT_MIN;
     const int hmax = __reduce_max_sync(FULL, hv);
-    if (hmax <= st.max && (p.Z < 0 || (p.ge >= 0 && st.max - hmax <= p.Z))) return false;
+    if (hmax <= st.max && hmax >= st.thr) return false;
     const unsigned whow = __ballot_sync(FULL, lane < NW && hv == hmax);
     const int srcw = 31 - __clz((int)whow);                                          // ties -> largest target index
     const int g = sm->scan_g[d & 1][srcw];
@@ -349,7 +356,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         inject(-1, UB{});                           // u(-1) = (W-1) & 1
     }
 
-    ScanState st = {0, 0, 0};                        // agatha_kernel.h:158-161
+    ScanState st = {0, 0, 0, scan_threshold(0, p)};   // agatha_kernel.h:158-161
     int stop = AGATHA_STOP_END, d_stop = pr.L;
     const bool has_phantom = pr.tcols > pr.tlen;
     const bool edge_lane = (gl == p.LW);
