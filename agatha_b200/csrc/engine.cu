@@ -35,6 +35,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 struct Shape { int C, NW; };
 static Shape shape_for(int W)
 {
+    if (W < 32 * 2) return {2, 1};
+    if (W < 32 * 4) return {4, 1};
     if (W < 32 * 8) return {8, 1};
     if (W < 32 * 16) return {16, 1};
     if (W < 32 * 24) return {24, 1};
@@ -62,7 +64,7 @@ static int launch_c(const JobArrays& ja, const KernelParams& kp, cudaStream_t st
     const bool wodd = kp.W & 1;
     if (wodd) {
         bool done = false;
-        int rc = launch_static_jw<C, NW, 7>(ja, kp, st, done);   if (done) return rc;
+        int rc = launch_static_jw<C, NW, (C < 8 ? C - 1 : 7)>(ja, kp, st, done);   if (done) return rc;
         rc = launch_static_jw<C, NW, 15>(ja, kp, st, done);      if (done) return rc;
         rc = launch_static_jw<C, NW, 23>(ja, kp, st, done);      if (done) return rc;
         rc = launch_static_jw<C, NW, 31>(ja, kp, st, done);      if (done) return rc;
@@ -164,6 +166,8 @@ int agatha_extend_device(const uint32_t* d_query_packed, const uint32_t* d_targe
     ja.n = (int)n_alns;
     const Shape sh = shape_for(kp.W);
     switch (sh.C * 100 + sh.NW) {
+        case 201: return launch_c<2, 1>(ja, kp, st);
+        case 401: return launch_c<4, 1>(ja, kp, st);
         case 801: return launch_c<8, 1>(ja, kp, st);
         case 1601: return launch_c<16, 1>(ja, kp, st);
         case 2401: return launch_c<24, 1>(ja, kp, st);

@@ -294,8 +294,8 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                                          int& out_score, int& out_qend, int& out_tend, int& out_stop, int& out_dstop)
 {
     const int gl = 32 * warp + lane;                 // lane index inside the group: owns cells g in [C*gl, C*gl + C)
-    static_assert(C % 8 == 0 && C <= 32, "cells per lane must be a multiple of 8");
-    constexpr int NWORD = C / 8;
+    static_assert((C % 8 == 0 || C == 2 || C == 4) && C <= 32, "cells per lane: 2, 4 or a multiple of 8");
+    constexpr int NWORD = (C + 7) / 8;
     using U0 = std::integral_constant<int, 0>;
     using U1 = std::integral_constant<int, 1>;
     using UA = std::integral_constant<int, WODD ? 1 : 0>;   // parity class of even anti-diagonals
@@ -396,7 +396,8 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         if ((nb & 7) == 0) rfeed = load_tword(pr, nb >> 3);
 #pragma unroll
         for (int w = 0; w < NWORD - 1; w++) Rw[w] = __funnelshift_r(Rw[w], Rw[w + 1], 4);
-        Rw[NWORD - 1] = __funnelshift_r(Rw[NWORD - 1], rfeed, 4);
+        if (C % 8 == 0) Rw[NWORD - 1] = __funnelshift_r(Rw[NWORD - 1], rfeed, 4);
+        else Rw[NWORD - 1] = (Rw[NWORD - 1] >> 4) | ((rfeed & 15u) << (4 * ((C - 1) & 7)));   // nibbles >= C stay zero
         rfeed >>= 4;
         rbot++;
     };
@@ -512,7 +513,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
 template <int C, int NW>
 struct KernelShape {
     static constexpr int threads = NW == 1 ? 128 : 32 * NW;
-    static constexpr int min_blocks = NW == 1 ? (C <= 24 ? 3 : 2) : (32 * NW * (C <= 16 ? 128 : (C <= 24 ? 168 : 255)) <= 32768 ? 2 : 1);
+    static constexpr int min_blocks = NW == 1 ? (C <= 4 ? 8 : (C <= 24 ? 3 : 2)) : (32 * NW * (C <= 16 ? 128 : (C <= 24 ? 168 : 255)) <= 32768 ? 2 : 1);
 };
 
 template <int C, int NW, bool WODD, int JWS>

@@ -44,6 +44,17 @@ def load_int_peak():
         return 18.6, "fallback 148 SM x 64 lanes x 1.965 GHz (SURVEY 8d planning figure)"
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE extension-kernel launch of this very workload, from the committed
+    ncu --set full capture (profiles/extend_kernel_bench_r01_ncu.json, made by build/prof_bench.sh)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "extend_kernel_bench_r01_ncu.json")) as f:
+            d = json.load(f)
+        return d["traffic_bytes_per_launch"], {k: d[k] for k in ("alu_pipe_pct", "fma_pipe_pct", "issue_active_pct", "source")}
+    except Exception:
+        return None, None
+
+
 def load_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -296,9 +307,10 @@ def main():
     hbm_peak, hbm_src = load_hbm_peak()
     achieved = OPS_PER_CELL * cells / (kms * 1e-3) / 1e12
     alg_bytes = int(((qlen.astype(np.int64) + 7) // 8 * 4 + (tlen.astype(np.int64) + 7) // 8 * 4 + 16 + 12).sum())
-    roofline = {"bound": "int_alu", "kernel": "agatha::extend_kernel<24,true,7>", "achieved": achieved, "peak": int_peak, "unit": "Tint-op/s", "frac": achieved / int_peak,
+    traffic, ncu_info = load_traffic() if n == 100000 else (None, None)
+    roofline = {"bound": "int_alu", "kernel": "agatha::extend_kernel<24,1,true,7>", "achieved": achieved, "peak": int_peak, "unit": "Tint-op/s", "frac": achieved / int_peak,
                 "peak_source": int_src, "ops_per_cell": OPS_PER_CELL, "cells_per_launch": cells, "kernel_ms": kms,
-                "gcups": cells / (kms * 1e-3) / 1e9, "traffic": None,
+                "gcups": cells / (kms * 1e-3) / 1e9, "traffic": traffic, "ncu": ncu_info,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                         "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak},
                 "note": "integer-ALU bound by design (SURVEY 8d): ~1.4e3 cell updates per input byte; achieved = 10 int32 ops x needed cells / extension-kernel time"}
