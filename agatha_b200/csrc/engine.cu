@@ -91,6 +91,7 @@ int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
     kp->tab_lo = m | (x << 8) | (x << 16) | (x << 24);
     kp->tab_hi = 0xffffffffu;
     kp->one = 1; kp->k32 = 32;
+    kp->force_generic = fast_table_ok(p) ? 0 : 1;
     return AGATHA_OK;
 }
 
@@ -151,7 +152,6 @@ int agatha_extend_device(const uint32_t* d_query_packed, const uint32_t* d_targe
     KernelParams kp;
     int rc = make_kernel_params(params, &kp);
     if (rc) return rc;
-    if (!fast_table_ok(params)) return set_error(AGATHA_EUNSUPPORTED, "match/mismatch outside the byte lookup table range");
     if (agatha_device_count() == 0) return set_error(AGATHA_ENODEV, "no CUDA device");
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(d_workspace, 0, AGATHA_WORKSPACE_BYTES, st);

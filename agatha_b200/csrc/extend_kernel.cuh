@@ -13,8 +13,8 @@
 // (one warp shuffle per step). The per-anti-diagonal maximum needed by the Z-drop test is a lane-local max of
 // (H*32+j) keys, one warp REDUX per step and a warp-uniform scalar update: the scan is exact per anti-diagonal,
 // so a terminated alignment stops at once and the warp pulls the next job (work redistribution on termination).
-// Per cell: IDP.4A (score lookup + add), IADD, VIMNMX3, 2x VIADDMNMX, LEA, 1/2 VIMNMX3  -- DPX max-plus ops on
-// the ALU pipe, the rest on the FMA pipe.
+// Per cell, ALU pipe: IDP.4A (score byte select + add), VIMNMX3 (H), 2x VIADDMNMX (E, F), 1/2 VIMNMX3 (tracking);
+// FMA pipe: IMAD for t = M - goe and for the tracking key. ncu on the bench launch: ALU pipe 78.7 % busy.
 #pragma once
 
 #include <cstdint>
@@ -41,6 +41,7 @@ struct KernelParams {
     unsigned tab_lo, tab_hi;         // PRMT lookup table: byte x -> score for code XOR x (fast alphabet)
     int LW, JW;                      // lane / cell index of k = +W  (global cell index g = W, u = 0)
     int one, k32;                    // the constants 1 and 32, opaque to ptxas: keep a*1+c and h*32+j on IMAD (FMA pipe)
+    int force_generic;               // match/mismatch do not fit the byte table: score every pair with compare/select
 };
 
 struct JobArrays {
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(KernelShape<C, NW>::threads, KernelShape<C, NW
 
         int score = 0, qend = 0, tend = 0, stop = AGATHA_STOP_END, dstop = 0;
         if (pr.qlen > 0 && pr.tlen > 0) {
-            if (has_rare_symbols(pr, lane)) run_pair<C, NW, WODD, JWS, true>(pr, p, lane, warp, sm, score, qend, tend, stop, dstop);
+            if (p.force_generic || has_rare_symbols(pr, lane)) run_pair<C, NW, WODD, JWS, true>(pr, p, lane, warp, sm, score, qend, tend, stop, dstop);
             else run_pair<C, NW, WODD, JWS, false>(pr, p, lane, warp, sm, score, qend, tend, stop, dstop);
         }
         if (lane == 0 && warp == 0) {

@@ -38,3 +38,14 @@ def test_extreme_shapes(oracle):
         exp = oracle.align_pairs(pairs, op.make_params(**pkw))
         for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
             assert (got[a] == exp[b]).all(), (pkw, a, got, exp)
+
+
+def test_scores_outside_the_byte_table_use_generic_scoring(oracle):
+    import agatha_b200 as ag
+    pairs = make_pairs(4321, 120, 5, 700, mixed=True)
+    for pkw in (dict(match=200, mismatch=300, gap_open=500, gap_extend=150, band_width=63, z_threshold=20000),
+                dict(match=1, mismatch=0, band_width=31), dict(match=0, mismatch=1, band_width=31, z_threshold=5)):
+        got = ag.align_pairs_device(pairs, ag.make_params(**pkw))
+        exp = oracle.align_pairs(pairs, op.make_params(**pkw))
+        for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
+            assert (got[a] == exp[b]).all(), (pkw, a)
