@@ -92,6 +92,11 @@ int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
     kp->tab_hi = 0xffffffffu;
     kp->one = 1; kp->k32 = 32;
     kp->force_generic = fast_table_ok(p) ? 0 : 1;
+    // 16-bit packed steady state (extend_kernel.cuh run_fast16): needs small scoring values so that the per-window drift
+    // bounds of its range monitor hold; AGATHA_S16=0 disables it (A/B measurements)
+    const char* env = getenv("AGATHA_S16");
+    kp->s16 = (!kp->force_generic && p->match >= 0 && p->match <= 100 && p->mismatch <= 100 && p->gap_open >= 0 && p->gap_extend >= 0 &&
+               p->gap_open + 2 * p->gap_extend <= 2000 && !(env && env[0] == '0')) ? 1 : 0;
     return AGATHA_OK;
 }
 

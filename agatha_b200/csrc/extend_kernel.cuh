@@ -41,6 +41,7 @@ struct KernelParams {
     unsigned tab_lo, tab_hi;         // PRMT lookup table: byte x -> score for code XOR x (fast alphabet)
     int LW, JW;                      // lane / cell index of k = +W  (global cell index g = W, u = 0)
     int one, k32;                    // the constants 1 and 32, opaque to ptxas: keep a*1+c and h*32+j on IMAD (FMA pipe)
+    int s16;                         // steady state may run on 16-bit packed state (scoring small enough, see engine.cu)
     int force_generic;               // match/mismatch do not fit the byte table: score every pair with compare/select
 };
 
@@ -131,6 +132,58 @@ __device__ __forceinline__ int step_cells(int (&H)[C], int (&E)[C], int (&F)[C],
         if (jj & 1) best = __vimax3_s32(best, pend, key); else pend = key;
     }
     if (C & 1) best = max(best, pend);
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same step on 16-bit packed state (steady state only): register jj of each array holds cell jj in its low half
+// and cell jj + C/2 in its high half, values relative to a per-alignment base, so one VIADDMNMX.S16x2 / VIMNMX3.S16x2
+// updates two cells (measured: same issue rate as the 32-bit forms, profiles/int_peak_r01.json).
+//   M and t are clamped at FLOOR16 by the same VIADDMNMX that computes them, which bounds every value from below and
+//   keeps dead (out-of-band) cells dead; run_pair's range monitor guarantees that no LIVE value ever gets near the clamp
+//   or near +32767, so inside this loop the arithmetic is identical to the 32-bit one.
+// Returns the packed running maximum of H (no index: the argmax is recovered lazily from a snapshot).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FLOOR16 = -30000;
+
+__device__ __forceinline__ unsigned pack16(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+__device__ __forceinline__ int lo16(unsigned x) { return (int)(short)(x & 0xffffu); }
+__device__ __forceinline__ int hi16(unsigned x) { return (int)x >> 16; }
+
+template <int C, int U>
+__device__ __forceinline__ unsigned step_cells16(unsigned (&H)[C / 2], unsigned (&E)[C / 2], unsigned (&F)[C / 2],
+                                                 const uint32_t (&Qw)[(C + 7) / 8], const uint32_t (&Rw)[(C + 7) / 8],
+                                                 unsigned edge_in, const KernelParams& p, unsigned mge2, unsigned mgoe2, unsigned floor2)
+{
+    constexpr int P = C / 2, NWORD = (C + 7) / 8;
+    unsigned sc[2 * NWORD];
+#pragma unroll
+    for (int w = 0; w < NWORD; w++) {
+        unsigned x = Qw[w] ^ Rw[w];
+        sc[2 * w] = prmt(p.tab_lo, p.tab_hi, x);
+        sc[2 * w + 1] = prmt(p.tab_lo, p.tab_hi, x >> 16);
+    }
+    unsigned best = 0x80008000u, pend = 0x80008000u;
+#pragma unroll
+    for (int t_ = 0; t_ < P; t_++) {
+        const int jj = (U == 0) ? (P - 1 - t_) : t_;          // same read-before-write order as step_cells
+        unsigned ein, fin;
+        if (U == 0) { ein = (jj == 0) ? edge_in : E[jj - 1]; fin = F[jj]; }
+        else        { ein = E[jj]; fin = (jj == P - 1) ? edge_in : F[jj + 1]; }
+        // sign-extended score pair: byte (a&3) of sc[a>>2] for cell a = jj, byte (b&3) of sc[b>>2] for cell b = jj + P
+        constexpr int dummy = 0; (void)dummy;
+        const int a = jj, b = jj + P;
+        const unsigned sel = (unsigned)(a & 3) | ((unsigned)((a & 3) | 8) << 4) | ((unsigned)(4 + (b & 3)) << 8) | ((unsigned)((4 + (b & 3)) | 8) << 12);
+        const unsigned s2 = prmt(sc[a >> 2], sc[b >> 2], sel);
+        const unsigned m = __viaddmax_s16x2(H[jj], s2, floor2);           // max(H(d-2,k) + s, FLOOR)
+        const unsigned h = __vimax3_s16x2(m, ein, fin);
+        const unsigned t = __viaddmax_s16x2(m, mgoe2, floor2);            // max(M - goe, FLOOR)
+        E[jj] = __viaddmax_s16x2(ein, mge2, t);
+        F[jj] = __viaddmax_s16x2(fin, mge2, t);
+        H[jj] = h;
+        if (t_ & 1) best = __vimax3_s16x2(best, pend, h); else pend = h;
+    }
+    if (P & 1) best = __vimax3_s16x2(best, pend, pend);
     return best;
 }
 
@@ -459,6 +512,155 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     const int d_tail = min(2 * pr.qlen - 2 - W, 2 * pr.tlen - 2 - W) + 1;
     const int d_fast_lo = (W + 2) & ~1;                                   // even, > W: no injection, band edges are real
     const int d_fast_hi = min(d_tail - 1, pr.L - 1) & ~1;                 // FAST pairs (d, d+1) need d+1 < d_tail and d+1 < L
+
+    // --- steady state on 16-bit packed state ---------------------------------------------------------------------
+    // Runs anti-diagonals [d, d_fast_hi) in one go (no slice of the reference can end the alignment in this range: the
+    // band-exit rule only fires after the band has left the matrix, i.e. beyond d_tail). State is converted at entry and
+    // exit. Returns 0: reached d_fast_hi; 1: Z-drop fired on anti-diagonal d; 2: values left the safe 16-bit range at d,
+    // state is back in the 32-bit arrays and the caller continues with the 32-bit loop.
+    constexpr bool CAN16 = !GENERIC && NW == 1 && JWS >= 0 && C % 8 == 0;
+    auto run_fast16 = [&](int& d) -> int {
+        constexpr int P = C / 2;
+        constexpr int JP = (JWS >= 0 ? JWS : 0) % P, JH = (JWS >= 0 ? JWS : 0) / P;   // register / half holding the cell k = +W
+        int base = st.max;                                                 // packed value = true value - base
+        unsigned A0[P], A1[P], AE[P], AF[P];
+        {
+            auto sat = [&](int x) { return max(min(x - base, 32767), FLOOR16); };     // dead cells (NEGBIG) land on FLOOR16
+#pragma unroll
+            for (int jj = 0; jj < P; jj++) {
+                A0[jj] = pack16(sat(H0[jj]), sat(H0[jj + P])); A1[jj] = pack16(sat(H1[jj]), sat(H1[jj + P]));
+                AE[jj] = pack16(sat(E[jj]), sat(E[jj + P]));   AF[jj] = pack16(sat(F[jj]), sat(F[jj + P]));
+            }
+        }
+        const unsigned floor2 = pack16(FLOOR16, FLOOR16);
+        const unsigned mge2 = pack16(-p.ge, -p.ge), mgoe2 = pack16(-p.goe, -p.goe);
+        // Between two range checks (32 anti-diagonals) the smallest live H falls by at most 16*mismatch and the largest rises
+        // by at most 16*match; M = H + s and t = M - goe must stay above the clamp, H + match below 32767.
+        const int low_ok = FLOOR16 + 17 * max(p.mismatch, 1) + p.goe + 64;
+        const int high_ok = 32767 - 17 * max(p.match, 0) - 64;
+        int neg16 = max(NEG16 - base, FLOOR16);                            // MINUS_INF2 as seen from `base`
+        int maxrel = st.max - base;
+        auto rel_thr = [&]() { return (st.thr == INT_MIN || st.thr == INT_MAX) ? st.thr : st.thr - base; };
+        int thrrel = rel_thr();
+        // the position of a new maximum is only needed by a later Z-drop test or at the end: keep a snapshot of the
+        // anti-diagonal and search it lazily instead of carrying an index through every cell update
+        unsigned S[P];
+#pragma unroll
+        for (int jj = 0; jj < P; jj++) S[jj] = 0u;
+        int snap_d = -1, snap_u = 0, snap_src = 0, snap_h = 0;
+
+        auto search = [&](const unsigned (&A)[P], int h) -> int {          // largest cell index whose value is h, -1 if none
+            int jl = -1, jh = -1;
+#pragma unroll
+            for (int jj = 0; jj < P; jj++) { if (lo16(A[jj]) == h) jl = jj; if (hi16(A[jj]) == h) jh = jj + P; }
+            return jh >= 0 ? jh : jl;
+        };
+        auto resolve = [&]() {
+            if (snap_d < 0) return;
+            const int jb = __shfl_sync(FULL, search(S, snap_h), snap_src);
+            const int k = -W + 2 * (C * snap_src + jb) + snap_u;
+            const int r = (snap_d + k) >> 1;
+            st.mt = r; st.mq = snap_d - r;
+            snap_d = -1;
+        };
+        auto unpack = [&]() {
+            auto unp = [&](int v) { return v <= FLOOR16 + 16 ? NEGBIG : v + base; };
+#pragma unroll
+            for (int jj = 0; jj < P; jj++) {
+                H0[jj] = unp(lo16(A0[jj])); H0[jj + P] = unp(hi16(A0[jj])); H1[jj] = unp(lo16(A1[jj])); H1[jj + P] = unp(hi16(A1[jj]));
+                E[jj] = unp(lo16(AE[jj]));  E[jj + P] = unp(hi16(AE[jj]));  F[jj] = unp(lo16(AF[jj]));  F[jj + P] = unp(hi16(AF[jj]));
+            }
+        };
+        // range monitor over the live H values (both parities) + rebasing; false = leave the packed loop
+        auto check_range = [&]() -> bool {
+            unsigned mn2 = 0x7fff7fffu, mx2 = 0x80008000u;
+#pragma unroll
+            for (int jj = 0; jj < P; jj++) {
+                unsigned x0 = A0[jj], x1 = A1[jj];
+                mx2 = __vimax3_s16x2(mx2, x0, x1);
+                // in the band-edge lane the cells beyond k = +W are dead by design: take them out of the minimum
+                // (parity 0: cell j is live iff j <= JW; parity 1: iff j < JW)
+                const bool l0 = jj <= JWS, h0 = jj + P <= JWS, l1 = jj < JWS, h1 = jj + P < JWS;
+                const unsigned e0 = (x0 & ((l0 ? 0xffffu : 0u) | (h0 ? 0xffff0000u : 0u))) | ((l0 ? 0u : 0x7fffu) | (h0 ? 0u : 0x7fff0000u));
+                const unsigned e1 = (x1 & ((l1 ? 0xffffu : 0u) | (h1 ? 0xffff0000u : 0u))) | ((l1 ? 0u : 0x7fffu) | (h1 ? 0u : 0x7fff0000u));
+                mn2 = __vimin3_s16x2(mn2, edge_lane ? e0 : x0, edge_lane ? e1 : x1);
+            }
+            int mn = min(lo16(mn2), hi16(mn2)), mx = max(lo16(mx2), hi16(mx2));
+            if (gl > p.LW) mn = 32767;                                       // lanes beyond the band hold nothing live
+            mn = __reduce_min_sync(FULL, mn);
+            mx = __reduce_max_sync(FULL, mx);
+            if (mn < low_ok || mx > high_ok) return false;
+            if (mx > 8192) {                                                 // re-centre: rare (every ~8192 score units)
+                const int delta = min(mx, mn - low_ok);
+                if (delta > 0) {
+                    // the packed add does not saturate: lift everything to FLOOR16 + delta first, then subtract
+                    const unsigned md2 = pack16(-delta, -delta), lift2 = pack16(FLOOR16 + delta, FLOOR16 + delta);
+                    auto shift_down = [&](unsigned x) { return __viaddmax_s16x2(__vimax3_s16x2(x, lift2, lift2), md2, floor2); };
+#pragma unroll
+                    for (int jj = 0; jj < P; jj++) {
+                        A0[jj] = shift_down(A0[jj]); A1[jj] = shift_down(A1[jj]); AE[jj] = shift_down(AE[jj]); AF[jj] = shift_down(AF[jj]);
+                    }
+                    base += delta;
+                    neg16 = max(NEG16 - base, FLOOR16);
+                    maxrel = st.max - base; thrrel = rel_thr();
+                }
+            }
+            return true;
+        };
+        // Termination Condition & Score Update (agatha_kernel.h:292-314) on the packed anti-diagonal
+        auto scan16 = [&](unsigned best2, const unsigned (&A)[P], int dd, int u) -> bool {
+            const int lane_h = max(lo16(best2), hi16(best2));
+            const int hrel = __reduce_max_sync(FULL, lane_h);
+            if (hrel <= maxrel && hrel >= thrrel) return false;
+            const unsigned who = __ballot_sync(FULL, lane_h == hrel);
+            const int src = 31 - __clz((int)who);                           // ties -> largest target index
+            if (hrel > maxrel) {
+#pragma unroll
+                for (int jj = 0; jj < P; jj++) S[jj] = A[jj];
+                snap_d = dd; snap_u = u; snap_src = src; snap_h = hrel;
+                st.max = hrel + base; st.thr = scan_threshold(st.max, p);
+                maxrel = hrel; thrrel = rel_thr();
+                return false;
+            }
+            resolve();                                                       // the test below needs (mt, mq)
+            const int jb = __shfl_sync(FULL, search(A, hrel), src);
+            return scan_update(st, hrel + base, C * src + jb, dd, u, p);
+        };
+        auto step16 = [&](int dd, auto u_tag) -> bool {
+            constexpr int U = decltype(u_tag)::value;
+            unsigned best2;
+            if (U == 0) {
+                unsigned x = __shfl_up_sync(FULL, AE[P - 1], 1);             // neighbour's (E[P-1], E[C-1])
+                if (lane == 0) x = (unsigned)neg16 << 16;                    // left of k = -W: MINUS_INF2
+                const unsigned ein = prmt(x, AE[P - 1], 0x5432);             // lo: neighbour's E[C-1], hi: own E[P-1]
+                best2 = step_cells16<C, 0>(A0, AE, AF, Qw, Rw, ein, p, mge2, mgoe2, floor2);
+                if (edge_lane) AE[JP] = JH ? ((AE[JP] & 0xffffu) | ((unsigned)FLOOR16 << 16)) : ((AE[JP] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu));
+                shift_ref();
+                return scan16(best2, A0, dd, 0);
+            } else {
+                unsigned y = __shfl_down_sync(FULL, AF[0], 1);               // neighbour's (F[0], F[P])
+                if (lane == 31) y = (unsigned)FLOOR16 & 0xffffu;             // right of the last lane: dead
+                const unsigned fin = prmt(AF[0], y, 0x5432);                 // lo: own F[P], hi: neighbour's F[0]
+                best2 = step_cells16<C, 1>(A1, AE, AF, Qw, Rw, fin, p, mge2, mgoe2, floor2);
+                if (edge_lane) AF[JP] = JH ? ((AF[JP] & 0xffffu) | ((unsigned)neg16 << 16)) : ((AF[JP] & 0xffff0000u) | ((unsigned)neg16 & 0xffffu));
+                shift_query();
+                return scan16(best2, A1, dd, 1);
+            }
+        };
+        if (!check_range()) return 2;                                        // 32-bit arrays untouched so far
+        int it = 0;
+#pragma unroll 1
+        for (; d < d_fast_hi; d += 2) {
+            if (it == 16) { it = 0; if (!check_range()) { resolve(); unpack(); return 2; } }
+            it++;
+            if (step16(d, UA{})) { resolve(); return 1; }
+            if (step16(d + 1, UB{})) { resolve(); d++; return 1; }
+        }
+        resolve();
+        unpack();
+        return 0;
+    };
+
     int d = 0;
     if (has_phantom) phantom_patch(0, UA{});
     if (NW > 1) {
@@ -467,7 +669,9 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         if (lane == 0) sm->edgeF[warp] = F[0];
         __syncthreads();
     }
-    for (int i = 0;; i += p.sw) {
+    bool allow16 = CAN16 && p.s16 != 0;
+    for (;;) {
+        const int i = ((d >> 3) / p.sw) * p.sw;          // the slice that contains anti-diagonal d
         bool wrap = false;
         int dend;
         if (i >= pr.total) {
@@ -476,17 +680,26 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             if (i != pr.total) break;
             wrap = true; dend = 8 * pr.total + 8;
         } else {
-            // slice bounds, agatha_kernel.h:183-191 (truncating division as in the reference)
-            int ss = max(0, i - pr.pq + 1);
-            ss = max(ss, (i * 8 + 8 - W) / 2 / 8);
-            int se = min(pr.pt - 1, i + p.sw - 1);
-            se = min(se, ((i + p.sw - 1) * 8 + 7 + W) / 2 / 8);
-            if (ss > se) { stop = AGATHA_STOP_BANDEXIT; d_stop = min(8 * i, pr.L); break; }
+            if (d == 8 * i) {
+                // slice bounds, agatha_kernel.h:183-191 (truncating division as in the reference)
+                int ss = max(0, i - pr.pq + 1);
+                ss = max(ss, (i * 8 + 8 - W) / 2 / 8);
+                int se = min(pr.pt - 1, i + p.sw - 1);
+                se = min(se, ((i + p.sw - 1) * 8 + 7 + W) / 2 / 8);
+                if (ss > se) { stop = AGATHA_STOP_BANDEXIT; d_stop = min(8 * i, pr.L); break; }
+            }
             dend = 8 * (i + p.sw);
         }
-        bool fired = false;
+        bool fired = false, reslice = false;
         while (d < dend) {
             if (d >= d_fast_lo && d < d_fast_hi) {
+                if (CAN16 && allow16) {
+                    const int rc = run_fast16(d);          // may cross slice boundaries: re-derive the slice afterwards
+                    if (rc == 1) { fired = true; break; }
+                    if (rc == 2) allow16 = false;
+                    reslice = true;
+                    break;
+                }
                 const int dlim = min(dend, d_fast_hi);
 #pragma unroll 1
                 for (; d < dlim; d += 2) {
@@ -502,6 +715,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             }
         }
         if (fired) { if (d < pr.L) { stop = AGATHA_STOP_ZDROP; d_stop = d + 1; } break; }
+        if (reslice) continue;
         if (wrap) break;
     }
     out_score = st.max; out_qend = st.mq; out_tend = st.mt; out_stop = stop; out_dstop = d_stop;

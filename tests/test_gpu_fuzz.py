@@ -49,3 +49,24 @@ def test_scores_outside_the_byte_table_use_generic_scoring(oracle):
         exp = oracle.align_pairs(pairs, op.make_params(**pkw))
         for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
             assert (got[a] == exp[b]).all(), (pkw, a)
+
+
+def test_packed_steady_state_rebasing_and_fallback(oracle):
+    """The 16-bit packed steady-state loop re-centres its values every time the score has grown by 8192 and leaves to the
+    32-bit loop when live values no longer fit: high match scores force many rebases, a disabled Z-drop on diverged pairs
+    forces the fallback, long pairs with the default scoring stay packed all the way."""
+    import agatha_b200 as ag
+    cases = [
+        (dict(match=5, mismatch=4, gap_open=6, gap_extend=2, band_width=751), make_pairs(71, 10, 9000, 14000, err=0.05)),        # ~50k scores: 6 rebases
+        (dict(match=3, mismatch=1, gap_open=12, gap_extend=1, band_width=383, slice_width=1, z_threshold=100), make_pairs(72, 60, 1500, 4000, mixed=True)),
+        (dict(match=1, mismatch=4, gap_open=6, gap_extend=2, band_width=751, z_threshold=-1), make_pairs(73, 8, 9000, 12000, err=0.1, tail=-1)),  # no Z-drop: values sink
+        (dict(match=2, mismatch=9, gap_open=12, gap_extend=3, band_width=511, z_threshold=30000), make_pairs(74, 8, 7000, 9000, err=0.3)),
+        (dict(band_width=751), make_pairs(75, 6, 28000, 31000, err=0.02)),                                                      # scores near 30k
+        (dict(match=100, mismatch=100, gap_open=1000, gap_extend=500, band_width=255), make_pairs(76, 20, 1500, 3000, err=0.1)),
+    ]
+    for pkw, pairs in cases:
+        got = ag.align_pairs_device(pairs, ag.make_params(**pkw))
+        exp = oracle.align_pairs(pairs, op.make_params(**pkw))
+        for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
+            bad = np.nonzero(got[a] != exp[b])[0]
+            assert len(bad) == 0, f"{pkw}: {a} differs for {len(bad)} pairs, first {bad[0]}: gpu {got[bad[0]]} oracle {exp[bad[0]]}"
