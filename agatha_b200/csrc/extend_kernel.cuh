@@ -352,6 +352,10 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     constexpr int NWORD = (C + 7) / 8;
     using U0 = std::integral_constant<int, 0>;
     using U1 = std::integral_constant<int, 1>;
+    using M0 = std::integral_constant<int, 0>;
+    using M1 = std::integral_constant<int, 1>;
+    using M2 = std::integral_constant<int, 2>;
+    using M3 = std::integral_constant<int, 3>;
     using UA = std::integral_constant<int, WODD ? 1 : 0>;   // parity class of even anti-diagonals
     using UB = std::integral_constant<int, WODD ? 0 : 1>;   // ... of odd ones
     const int W = p.W;
@@ -457,12 +461,16 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     };
 
     // one anti-diagonal; returns true when Z-drop fires on it
-    auto do_step = [&](int d, bool scan, auto u_tag, auto fast_tag) -> bool {
+    // MODE 0 FAST: every in-band cell is inside the matrix. MODE 1 PRO: near edges only -- inject the boundary cells; what
+    // lies beyond them is dead (NEGBIG), so the maximum needs no mask. MODE 2 TAIL: far edges only -- mask the maximum,
+    // patch the padding columns. MODE 3: both (pairs shorter than the band).
+    auto do_step = [&](int d, bool scan, auto u_tag, auto mode_tag) -> bool {
         constexpr int U = decltype(u_tag)::value;
-        constexpr bool FAST = decltype(fast_tag)::value;
+        constexpr int MODE = decltype(mode_tag)::value;
+        constexpr bool FAST = MODE == 0, MASK = MODE >= 2, INJECT = MODE == 1 || MODE == 3;
         using UN = std::integral_constant<int, 1 - U>;
         int jlo = 0, jhi = C - 1;
-        if (!FAST) {
+        if (MASK) {
             const int klo = max(-W, max(-d, d - 2 * (pr.qlen - 1)));
             const int khi = min(W, min(d, 2 * (pr.tcols - 1) - d));
             const int k0 = -W + 2 * C * gl + U;
@@ -478,7 +486,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 if (NW == 1 || warp == 0) ein = (FAST || d > W) ? NEG16 : ((d == W) ? (-(p.goe + p.ge * W) - p.goe) : NEGBIG);
                 else ein = sm->edgeE[warp - 1];
             }
-            best = step_cells<C, 0, !FAST, GENERIC>(H0, E, F, Qw, Rw, ein, p, jlo, jhi);
+            best = step_cells<C, 0, MASK, GENERIC>(H0, E, F, Qw, Rw, ein, p, jlo, jhi);
             if (JWS >= 0) { if (edge_lane) E[JWS >= 0 ? JWS : 0] = NEGBIG; } else poke<C>(E, jw_dyn, NEGBIG);   // nothing may leak into k = W+1
             shift_ref();
         } else {
@@ -487,15 +495,14 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 if (NW == 1 || warp == NW - 1) fin = NEGBIG;
                 else fin = sm->edgeF[warp + 1];
             }
-            best = step_cells<C, 1, !FAST, GENERIC>(H1, E, F, Qw, Rw, fin, p, jlo, jhi);
+            best = step_cells<C, 1, MASK, GENERIC>(H1, E, F, Qw, Rw, fin, p, jlo, jhi);
             // k = W reads MINUS_INF2 from outside the band (agatha_kernel.h:138); F(0,W) is injected below at d = W-1
             { const int v = (FAST || d + 1 > W) ? NEG16 : NEGBIG; if (JWS >= 0) { if (edge_lane) F[JWS >= 0 ? JWS : 0] = v; } else poke<C>(F, jw_dyn, v); }
             shift_query();
         }
-        if (!FAST) {
-            if (d < W) inject(d, u_tag);
-            if (has_phantom) phantom_patch(d + 1, UN{});     // inputs of the next anti-diagonal, before they are handed over
-        }
+        if (INJECT) { if (d < W) inject(d, u_tag); }
+        // padding columns enter the band only after d_tail, i.e. never right after a PRO step
+        if (MASK) { if (has_phantom) phantom_patch(d + 1, UN{}); }    // inputs of the next anti-diagonal, before they are handed over
         if (NW == 1) {
             if (!scan) return false;
             return scan_diag<C>(st, best, d, U, lane, p);
@@ -607,54 +614,75 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             }
             return true;
         };
-        // Termination Condition & Score Update (agatha_kernel.h:292-314) on the packed anti-diagonal
-        auto scan16 = [&](unsigned best2, const unsigned (&A)[P], int dd, int u) -> bool {
+        // Termination Condition & Score Update (agatha_kernel.h:292-314) on the packed anti-diagonal, split in two so that
+        // the hot loop only carries the common cases. scan_fast: nothing to do, or a new maximum (snapshot for the lazy
+        // argmax); returns true when the anti-diagonal might fire Z-drop -> scan_slow, outside the hot loop.
+        int ev_lane_h = 0, ev_hrel = 0;
+        auto scan_fast = [&](unsigned best2, const unsigned (&A)[P], int dd, int u) -> bool {
             const int lane_h = max(lo16(best2), hi16(best2));
             const int hrel = __reduce_max_sync(FULL, lane_h);
             if (hrel <= maxrel && hrel >= thrrel) return false;
-            const unsigned who = __ballot_sync(FULL, lane_h == hrel);
-            const int src = 31 - __clz((int)who);                           // ties -> largest target index
             if (hrel > maxrel) {
+                const unsigned who = __ballot_sync(FULL, lane_h == hrel);
 #pragma unroll
                 for (int jj = 0; jj < P; jj++) S[jj] = A[jj];
-                snap_d = dd; snap_u = u; snap_src = src; snap_h = hrel;
+                snap_d = dd; snap_u = u; snap_src = 31 - __clz((int)who); snap_h = hrel;   // ties -> largest target index
                 st.max = hrel + base; st.thr = scan_threshold(st.max, p);
                 maxrel = hrel; thrrel = rel_thr();
                 return false;
             }
-            resolve();                                                       // the test below needs (mt, mq)
-            const int jb = __shfl_sync(FULL, search(A, hrel), src);
-            return scan_update(st, hrel + base, C * src + jb, dd, u, p);
+            ev_lane_h = lane_h; ev_hrel = hrel;
+            return true;
         };
+        auto scan_slow = [&](const unsigned (&A)[P], int dd, int u) -> bool {
+            resolve();                                                       // the test needs (mt, mq)
+            const unsigned who = __ballot_sync(FULL, ev_lane_h == ev_hrel);
+            const int src = 31 - __clz((int)who);
+            const int jb = __shfl_sync(FULL, search(A, ev_hrel), src);
+            return scan_update(st, ev_hrel + base, C * src + jb, dd, u, p);
+        };
+        // one packed anti-diagonal; true = scan_slow must look at it
         auto step16 = [&](int dd, auto u_tag) -> bool {
             constexpr int U = decltype(u_tag)::value;
-            unsigned best2;
             if (U == 0) {
                 unsigned x = __shfl_up_sync(FULL, AE[P - 1], 1);             // neighbour's (E[P-1], E[C-1])
                 if (lane == 0) x = (unsigned)neg16 << 16;                    // left of k = -W: MINUS_INF2
                 const unsigned ein = prmt(x, AE[P - 1], 0x5432);             // lo: neighbour's E[C-1], hi: own E[P-1]
-                best2 = step_cells16<C, 0>(A0, AE, AF, Qw, Rw, ein, p, mge2, mgoe2, floor2);
+                const unsigned best2 = step_cells16<C, 0>(A0, AE, AF, Qw, Rw, ein, p, mge2, mgoe2, floor2);
                 if (edge_lane) AE[JP] = JH ? ((AE[JP] & 0xffffu) | ((unsigned)FLOOR16 << 16)) : ((AE[JP] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu));
                 shift_ref();
-                return scan16(best2, A0, dd, 0);
+                return scan_fast(best2, A0, dd, 0);
             } else {
                 unsigned y = __shfl_down_sync(FULL, AF[0], 1);               // neighbour's (F[0], F[P])
                 if (lane == 31) y = (unsigned)FLOOR16 & 0xffffu;             // right of the last lane: dead
                 const unsigned fin = prmt(AF[0], y, 0x5432);                 // lo: own F[P], hi: neighbour's F[0]
-                best2 = step_cells16<C, 1>(A1, AE, AF, Qw, Rw, fin, p, mge2, mgoe2, floor2);
+                const unsigned best2 = step_cells16<C, 1>(A1, AE, AF, Qw, Rw, fin, p, mge2, mgoe2, floor2);
                 if (edge_lane) AF[JP] = JH ? ((AF[JP] & 0xffffu) | ((unsigned)neg16 << 16)) : ((AF[JP] & 0xffff0000u) | ((unsigned)neg16 & 0xffffu));
                 shift_query();
-                return scan16(best2, A1, dd, 1);
+                return scan_fast(best2, A1, dd, 1);
             }
         };
         if (!check_range()) return 2;                                        // 32-bit arrays untouched so far
-        int it = 0;
+        for (;;) {
+            // hot loop: up to 32 anti-diagonals between two range checks, left early only for a possible Z-drop
+            const int dchunk = min(d_fast_hi, d + 32);
+            int ev = 0;
 #pragma unroll 1
-        for (; d < d_fast_hi; d += 2) {
-            if (it == 16) { it = 0; if (!check_range()) { resolve(); unpack(); return 2; } }
-            it++;
-            if (step16(d, UA{})) { resolve(); return 1; }
-            if (step16(d + 1, UB{})) { resolve(); d++; return 1; }
+            for (; d < dchunk; d += 2) {
+                if (step16(d, UA{})) { ev = 1; break; }
+                if (step16(d + 1, UB{})) { ev = 2; break; }
+            }
+            if (ev == 1) {
+                if (WODD ? scan_slow(A1, d, 1) : scan_slow(A0, d, 0)) { resolve(); return 1; }
+                if (step16(d + 1, UB{})) ev = 2;                             // finish the pair (cold copy of the second step)
+                else d += 2;
+            }
+            if (ev == 2) {
+                if (WODD ? scan_slow(A0, d + 1, 0) : scan_slow(A1, d + 1, 1)) { resolve(); d++; return 1; }
+                d += 2;
+            }
+            if (d >= d_fast_hi) break;
+            if (!check_range()) { resolve(); unpack(); return 2; }
         }
         resolve();
         unpack();
@@ -703,14 +731,20 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 const int dlim = min(dend, d_fast_hi);
 #pragma unroll 1
                 for (; d < dlim; d += 2) {
-                    if (do_step(d, true, UA{}, std::true_type{})) { fired = true; break; }
-                    if (do_step(d + 1, true, UB{}, std::true_type{})) { fired = true; d++; break; }
+                    if (do_step(d, true, UA{}, M0{})) { fired = true; break; }
+                    if (do_step(d + 1, true, UB{}, M0{})) { fired = true; d++; break; }
                 }
                 if (fired) break;
             } else {
                 if (has_phantom && d == d_fast_hi && d > 0) phantom_patch(d, UA{});   // first SLOW step after the FAST run
-                if (do_step(d, wrap || d < pr.L, UA{}, std::false_type{})) { fired = true; break; }
-                if (do_step(d + 1, wrap || d + 1 < pr.L, UB{}, std::false_type{})) { fired = true; d++; break; }
+                const bool s0 = wrap || d < pr.L, s1 = wrap || d + 1 < pr.L;
+                const bool far = d + 1 >= d_tail, near = d < W;                      // which matrix edges touch this pair of steps
+                bool f0, f1 = false;
+                if (!far)       { f0 = do_step(d, s0, UA{}, M1{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M1{}); }
+                else if (!near) { f0 = do_step(d, s0, UA{}, M2{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M2{}); }
+                else            { f0 = do_step(d, s0, UA{}, M3{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M3{}); }
+                if (f0) { fired = true; break; }
+                if (f1) { fired = true; d++; break; }
                 d += 2;
             }
         }
