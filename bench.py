@@ -313,7 +313,7 @@ def main():
                 "gcups": cells / (kms * 1e-3) / 1e9, "traffic": traffic, "ncu": ncu_info,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                         "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak},
-                "note": "integer-ALU bound by design (SURVEY 8d): ~1.4e3 cell updates per input byte; achieved = 10 int32 ops x needed cells / extension-kernel time"}
+                "note": "integer-ALU bound by design (SURVEY 8d): ~1.4e3 cell updates per input byte; achieved = 10 int32 ops x needed cells / extension-kernel time. frac can exceed 1: the accounting constant describes a 32-bit scalar formulation, the steady state runs on 16-bit packed DPX ops (two cells per instruction, ~3.5 ALU instructions per cell); the hardware reading is ncu.alu_pipe_pct"}
 
     # ---- e2e leg: host buffers through the C ABI (staging memcpy + H2D + pack + kernel + D2H per step)
     e2e_steps = max(1, min(args.steps, 3))
