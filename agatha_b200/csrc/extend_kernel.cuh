@@ -543,7 +543,9 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         const unsigned mge2 = pack16(-p.ge, -p.ge), mgoe2 = pack16(-p.goe, -p.goe);
         // Between two range checks (32 anti-diagonals) the smallest live H falls by at most 16*mismatch and the largest rises
         // by at most 16*match; M = H + s and t = M - goe must stay above the clamp, H + match below 32767.
-        const int low_ok = FLOOR16 + 17 * max(p.mismatch, 1) + p.goe + 64;
+        // Dead (out-of-band) cells creep upwards by `match` whenever their bases happen to be equal (nothing else feeds them):
+        // they are pushed back to the floor at every range check, so they stay below FLOOR16 + 16*match < low_ok.
+        const int low_ok = FLOOR16 + 17 * max(max(p.mismatch, p.match), 1) + p.goe + 64;
         const int high_ok = 32767 - 17 * max(p.match, 0) - 64;
         int neg16 = max(NEG16 - base, FLOOR16);                            // MINUS_INF2 as seen from `base`
         int maxrel = st.max - base;
@@ -570,26 +572,55 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             st.mt = r; st.mq = snap_d - r;
             snap_d = -1;
         };
+        // which halves of register jj are live in the band-edge lane (cell j live iff j <= JW for parity 0 / E, j < JW for
+        // parity 1 / F ... E is produced by parity-1 cells for parity-0 consumers and vice versa; being conservative costs
+        // nothing: a half is treated as dead only if its cell index is beyond JW for BOTH parities)
+        auto keep_mask = [&](int jj, bool strict) -> unsigned {            // strict: live iff j < JW, else j <= JW
+            const bool lo = strict ? (jj < JWS) : (jj <= JWS), hi = strict ? (jj + P < JWS) : (jj + P <= JWS);
+            return (lo ? 0xffffu : 0u) | (hi ? 0xffff0000u : 0u);
+        };
         auto unpack = [&]() {
-            auto unp = [&](int v) { return v <= FLOOR16 + 16 ? NEGBIG : v + base; };
+            const bool dead_lane = gl > p.LW;
+            auto unp = [&](unsigned x, bool hi, unsigned keep) {
+                const int v = (hi ? hi16(x) : lo16(x)) + base;
+                const bool live = !dead_lane && (!edge_lane || (keep & (hi ? 0xffff0000u : 0xffffu)));
+                return live ? v : NEGBIG;
+            };
 #pragma unroll
             for (int jj = 0; jj < P; jj++) {
-                H0[jj] = unp(lo16(A0[jj])); H0[jj + P] = unp(hi16(A0[jj])); H1[jj] = unp(lo16(A1[jj])); H1[jj + P] = unp(hi16(A1[jj]));
-                E[jj] = unp(lo16(AE[jj]));  E[jj + P] = unp(hi16(AE[jj]));  F[jj] = unp(lo16(AF[jj]));  F[jj + P] = unp(hi16(AF[jj]));
+                const unsigned k0 = keep_mask(jj, false), k1 = keep_mask(jj, true);
+                H0[jj] = unp(A0[jj], false, k0); H0[jj + P] = unp(A0[jj], true, k0);
+                H1[jj] = unp(A1[jj], false, k1); H1[jj + P] = unp(A1[jj], true, k1);
+                // The loop always leaves after a UB step. E then feeds the other parity's cells and is live for j < JW only
+                // (E[JW] is the dead hand-over into k = W+1); F is live for j <= JW.
+                E[jj] = unp(AE[jj], false, k1); E[jj + P] = unp(AE[jj], true, k1);
+                F[jj] = unp(AF[jj], false, k0); F[jj + P] = unp(AF[jj], true, k0);
             }
+            // after a parity-1 step F[JW] is not a DP value but the MINUS_INF2 that k = +W reads from outside the band
+            if (!WODD && edge_lane) F[JWS >= 0 ? JWS : 0] = NEG16;
         };
         // range monitor over the live H values (both parities) + rebasing; false = leave the packed loop
         auto check_range = [&]() -> bool {
+            // push the dead positions back to the floor (lanes beyond the band; in the band-edge lane the cells beyond k = +W)
+            const bool dead_lane = gl > p.LW;
+#pragma unroll
+            for (int jj = 0; jj < P; jj++) {
+                const unsigned k0 = keep_mask(jj, false), k1 = keep_mask(jj, true), kd = k0 & k1;
+                if (dead_lane) { A0[jj] = floor2; A1[jj] = floor2; AE[jj] = floor2; AF[jj] = floor2; }
+                else if (edge_lane) {
+                    A0[jj] = (A0[jj] & k0) | (floor2 & ~k0); A1[jj] = (A1[jj] & k1) | (floor2 & ~k1);
+                    AE[jj] = (AE[jj] & k0) | (floor2 & ~k0); AF[jj] = (AF[jj] & k0) | (floor2 & ~k0);
+                    (void)kd;
+                }
+            }
             unsigned mn2 = 0x7fff7fffu, mx2 = 0x80008000u;
 #pragma unroll
             for (int jj = 0; jj < P; jj++) {
                 unsigned x0 = A0[jj], x1 = A1[jj];
                 mx2 = __vimax3_s16x2(mx2, x0, x1);
-                // in the band-edge lane the cells beyond k = +W are dead by design: take them out of the minimum
-                // (parity 0: cell j is live iff j <= JW; parity 1: iff j < JW)
-                const bool l0 = jj <= JWS, h0 = jj + P <= JWS, l1 = jj < JWS, h1 = jj + P < JWS;
-                const unsigned e0 = (x0 & ((l0 ? 0xffffu : 0u) | (h0 ? 0xffff0000u : 0u))) | ((l0 ? 0u : 0x7fffu) | (h0 ? 0u : 0x7fff0000u));
-                const unsigned e1 = (x1 & ((l1 ? 0xffffu : 0u) | (h1 ? 0xffff0000u : 0u))) | ((l1 ? 0u : 0x7fffu) | (h1 ? 0u : 0x7fff0000u));
+                // dead cells are out of the minimum: force their halves to +32767
+                const unsigned k0 = keep_mask(jj, false), k1 = keep_mask(jj, true);
+                const unsigned e0 = (x0 & k0) | (0x7fff7fffu & ~k0), e1 = (x1 & k1) | (0x7fff7fffu & ~k1);
                 mn2 = __vimin3_s16x2(mn2, edge_lane ? e0 : x0, edge_lane ? e1 : x1);
             }
             int mn = min(lo16(mn2), hi16(mn2)), mx = max(lo16(mx2), hi16(mx2));

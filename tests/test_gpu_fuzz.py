@@ -70,3 +70,28 @@ def test_packed_steady_state_rebasing_and_fallback(oracle):
         for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
             bad = np.nonzero(got[a] != exp[b])[0]
             assert len(bad) == 0, f"{pkw}: {a} differs for {len(bad)} pairs, first {bad[0]}: gpu {got[bad[0]]} oracle {exp[bad[0]]}"
+
+
+def test_off_band_repeat_does_not_leak_into_the_band(oracle):
+    """Dead cells just outside the band see a perfect repeat for tens of thousands of anti-diagonals (they gain `match`
+    per matching pair while nothing else feeds them); in the 16-bit packed loop they sit only 30000 below live values, so
+    they must be pushed back regularly. Target = unit repeated; query = the same shifted by one period > band width."""
+    import agatha_b200 as ag
+    rng = np.random.default_rng(99)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    pairs = []
+    for period, W in ((800, 751), (300, 255), (1100, 1023)):
+        unit = acgt[rng.integers(0, 4, period)]
+        t = np.tile(unit, 40000 // period + 2)[:40000]
+        noise = acgt[rng.integers(0, 4, 40000)]
+        q = t.copy()
+        bad = rng.random(40000) < 0.30                     # the in-band alignment is poor but alive ...
+        q[bad] = noise[bad]
+        q = np.concatenate([q[period:], unit])             # ... while diagonal offset = period matches perfectly
+        pairs.append((W, q, t))
+    for W, q, t in pairs:
+        for pkw in (dict(band_width=W, z_threshold=-1), dict(band_width=W, z_threshold=20000, match=2, mismatch=2)):
+            got = ag.align_pairs_device([(q, t)], ag.make_params(**pkw))
+            exp = oracle.align_pairs([(q, t)], op.make_params(**pkw))
+            for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
+                assert got[a][0] == exp[b][0], (pkw, a, got, exp)
