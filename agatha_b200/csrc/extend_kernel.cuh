@@ -139,21 +139,30 @@ __device__ __forceinline__ int step_cells(int (&H)[C], int (&E)[C], int (&F)[C],
 // The same step on 16-bit packed state (steady state only): register jj of each array holds cell jj in its low half
 // and cell jj + C/2 in its high half, values relative to a per-alignment base, so one VIADDMNMX.S16x2 / VIMNMX3.S16x2
 // updates two cells (measured: same issue rate as the 32-bit forms, profiles/int_peak_r01.json).
-//   M and t are clamped at FLOOR16 by the same VIADDMNMX that computes them, which bounds every value from below and
-//   keeps dead (out-of-band) cells dead; run_pair's range monitor guarantees that no LIVE value ever gets near the clamp
-//   or near +32767, so inside this loop the arithmetic is identical to the 32-bit one.
+//   M is clamped at FLOOR16 by the same VIADDMNMX that computes it, which bounds every value from below (t >= FLOOR - goe,
+//   E,F >= t) and keeps dead (out-of-band) cells near the floor; run_pair's range monitor guarantees that no LIVE value
+//   ever gets near the clamp or the top of the range, so inside this loop the arithmetic is identical to the 32-bit one
+//   (DESIGN.md section 2).
 // Returns the packed running maximum of H (no index: the argmax is recovered lazily from a snapshot).
 // ---------------------------------------------------------------------------------------------------------------
+// Representation: stored half = (value - base) + BIAS16 as an UNSIGNED 16-bit number, FLOOR16 <= value - base <= TOP16.
+// Unsigned, because then every half is >= FLOORU16 > goe and t = M - goe can be ONE 32-bit IMAD on the (idle) FMA pipe:
+// no half can borrow from its neighbour. VIADDMNMX.U16x2 adds modulo 2^16 (checked on a B200), so the sign-extended
+// negative scores and -ge work as two's complement addends.
 constexpr int FLOOR16 = -30000;
+constexpr int BIAS16 = 34000;
+constexpr int TOP16 = 65535 - BIAS16;                    // 31535
+constexpr unsigned FLOORU16 = (unsigned)(FLOOR16 + BIAS16);   // 4000
 
-__device__ __forceinline__ unsigned pack16(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
-__device__ __forceinline__ int lo16(unsigned x) { return (int)(short)(x & 0xffffu); }
-__device__ __forceinline__ int hi16(unsigned x) { return (int)x >> 16; }
+__device__ __forceinline__ unsigned pack16(int lo, int hi) { return ((unsigned)(lo + BIAS16) & 0xffffu) | ((unsigned)(hi + BIAS16) << 16); }
+__device__ __forceinline__ unsigned pack16raw(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }   // two's complement halves
+__device__ __forceinline__ int lo16(unsigned x) { return (int)(x & 0xffffu) - BIAS16; }
+__device__ __forceinline__ int hi16(unsigned x) { return (int)(x >> 16) - BIAS16; }
 
 template <int C, int U>
 __device__ __forceinline__ unsigned step_cells16(unsigned (&H)[C / 2], unsigned (&E)[C / 2], unsigned (&F)[C / 2],
                                                  const uint32_t (&Qw)[(C + 7) / 8], const uint32_t (&Rw)[(C + 7) / 8],
-                                                 unsigned edge_in, const KernelParams& p, unsigned mge2, unsigned mgoe2, unsigned floor2)
+                                                 unsigned edge_in, const KernelParams& p, unsigned mge2, int mgoe32, unsigned floor2)
 {
     constexpr int P = C / 2, NWORD = (C + 7) / 8;
     unsigned sc[2 * NWORD];
@@ -163,7 +172,7 @@ __device__ __forceinline__ unsigned step_cells16(unsigned (&H)[C / 2], unsigned 
         sc[2 * w] = prmt(p.tab_lo, p.tab_hi, x);
         sc[2 * w + 1] = prmt(p.tab_lo, p.tab_hi, x >> 16);
     }
-    unsigned best = 0x80008000u, pend = 0x80008000u;
+    unsigned best = 0u, pend = 0u;
 #pragma unroll
     for (int t_ = 0; t_ < P; t_++) {
         const int jj = (U == 0) ? (P - 1 - t_) : t_;          // same read-before-write order as step_cells
@@ -171,19 +180,18 @@ __device__ __forceinline__ unsigned step_cells16(unsigned (&H)[C / 2], unsigned 
         if (U == 0) { ein = (jj == 0) ? edge_in : E[jj - 1]; fin = F[jj]; }
         else        { ein = E[jj]; fin = (jj == P - 1) ? edge_in : F[jj + 1]; }
         // sign-extended score pair: byte (a&3) of sc[a>>2] for cell a = jj, byte (b&3) of sc[b>>2] for cell b = jj + P
-        constexpr int dummy = 0; (void)dummy;
         const int a = jj, b = jj + P;
         const unsigned sel = (unsigned)(a & 3) | ((unsigned)((a & 3) | 8) << 4) | ((unsigned)(4 + (b & 3)) << 8) | ((unsigned)((4 + (b & 3)) | 8) << 12);
         const unsigned s2 = prmt(sc[a >> 2], sc[b >> 2], sel);
-        const unsigned m = __viaddmax_s16x2(H[jj], s2, floor2);           // max(H(d-2,k) + s, FLOOR)
-        const unsigned h = __vimax3_s16x2(m, ein, fin);
-        const unsigned t = __viaddmax_s16x2(m, mgoe2, floor2);            // max(M - goe, FLOOR)
-        E[jj] = __viaddmax_s16x2(ein, mge2, t);
-        F[jj] = __viaddmax_s16x2(fin, mge2, t);
+        const unsigned m = __viaddmax_u16x2(H[jj], s2, floor2);           // max(H(d-2,k) + s, FLOOR)
+        const unsigned h = __vimax3_u16x2(m, ein, fin);
+        const unsigned t = (unsigned)imad((int)m, p.one, mgoe32);          // M - goe in both halves: no borrow, m >= FLOORU16 > goe
+        E[jj] = __viaddmax_u16x2(ein, mge2, t);
+        F[jj] = __viaddmax_u16x2(fin, mge2, t);
         H[jj] = h;
-        if (t_ & 1) best = __vimax3_s16x2(best, pend, h); else pend = h;
+        if (t_ & 1) best = __vimax3_u16x2(best, pend, h); else pend = h;
     }
-    if (P & 1) best = __vimax3_s16x2(best, pend, pend);
+    if (P & 1) best = __vimax3_u16x2(best, pend, pend);
     return best;
 }
 
@@ -532,7 +540,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         int base = st.max;                                                 // packed value = true value - base
         unsigned A0[P], A1[P], AE[P], AF[P];
         {
-            auto sat = [&](int x) { return max(min(x - base, 32767), FLOOR16); };     // dead cells (NEGBIG) land on FLOOR16
+            auto sat = [&](int x) { return max(min(x - base, TOP16), FLOOR16); };     // dead cells (NEGBIG) land on FLOOR16
 #pragma unroll
             for (int jj = 0; jj < P; jj++) {
                 A0[jj] = pack16(sat(H0[jj]), sat(H0[jj + P])); A1[jj] = pack16(sat(H1[jj]), sat(H1[jj + P]));
@@ -540,13 +548,14 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             }
         }
         const unsigned floor2 = pack16(FLOOR16, FLOOR16);
-        const unsigned mge2 = pack16(-p.ge, -p.ge), mgoe2 = pack16(-p.goe, -p.goe);
+        const unsigned mge2 = pack16raw(-p.ge, -p.ge);                    // two's complement halves
+        const int mgoe32 = -(int)((unsigned)p.goe | ((unsigned)p.goe << 16));   // subtracts goe from both halves at once
         // Between two range checks (32 anti-diagonals) the smallest live H falls by at most 16*mismatch and the largest rises
         // by at most 16*match; M = H + s and t = M - goe must stay above the clamp, H + match below 32767.
         // Dead (out-of-band) cells creep upwards by `match` whenever their bases happen to be equal (nothing else feeds them):
         // they are pushed back to the floor at every range check, so they stay below FLOOR16 + 16*match < low_ok.
         const int low_ok = FLOOR16 + 17 * max(max(p.mismatch, p.match), 1) + p.goe + 64;
-        const int high_ok = 32767 - 17 * max(p.match, 0) - 64;
+        const int high_ok = TOP16 - 17 * max(p.match, 0) - 64;
         int neg16 = max(NEG16 - base, FLOOR16);                            // MINUS_INF2 as seen from `base`
         int maxrel = st.max - base;
         auto rel_thr = [&]() { return (st.thr == INT_MIN || st.thr == INT_MAX) ? st.thr : st.thr - base; };
@@ -613,18 +622,18 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                     (void)kd;
                 }
             }
-            unsigned mn2 = 0x7fff7fffu, mx2 = 0x80008000u;
+            unsigned mn2 = 0xffffffffu, mx2 = 0u;
 #pragma unroll
             for (int jj = 0; jj < P; jj++) {
                 unsigned x0 = A0[jj], x1 = A1[jj];
-                mx2 = __vimax3_s16x2(mx2, x0, x1);
-                // dead cells are out of the minimum: force their halves to +32767
+                mx2 = __vimax3_u16x2(mx2, x0, x1);
+                // dead cells are out of the minimum: force their halves to the largest value
                 const unsigned k0 = keep_mask(jj, false), k1 = keep_mask(jj, true);
-                const unsigned e0 = (x0 & k0) | (0x7fff7fffu & ~k0), e1 = (x1 & k1) | (0x7fff7fffu & ~k1);
-                mn2 = __vimin3_s16x2(mn2, edge_lane ? e0 : x0, edge_lane ? e1 : x1);
+                const unsigned e0 = x0 | ~k0, e1 = x1 | ~k1;
+                mn2 = __vimin3_u16x2(mn2, edge_lane ? e0 : x0, edge_lane ? e1 : x1);
             }
             int mn = min(lo16(mn2), hi16(mn2)), mx = max(lo16(mx2), hi16(mx2));
-            if (gl > p.LW) mn = 32767;                                       // lanes beyond the band hold nothing live
+            if (gl > p.LW) mn = TOP16;                                       // lanes beyond the band hold nothing live
             mn = __reduce_min_sync(FULL, mn);
             mx = __reduce_max_sync(FULL, mx);
             if (mn < low_ok || mx > high_ok) return false;
@@ -632,8 +641,8 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 const int delta = min(mx, mn - low_ok);
                 if (delta > 0) {
                     // the packed add does not saturate: lift everything to FLOOR16 + delta first, then subtract
-                    const unsigned md2 = pack16(-delta, -delta), lift2 = pack16(FLOOR16 + delta, FLOOR16 + delta);
-                    auto shift_down = [&](unsigned x) { return __viaddmax_s16x2(__vimax3_s16x2(x, lift2, lift2), md2, floor2); };
+                    const unsigned md2 = pack16raw(-delta, -delta), lift2 = pack16(FLOOR16 + delta, FLOOR16 + delta);
+                    auto shift_down = [&](unsigned x) { return __viaddmax_u16x2(__vimax3_u16x2(x, lift2, lift2), md2, floor2); };
 #pragma unroll
                     for (int jj = 0; jj < P; jj++) {
                         A0[jj] = shift_down(A0[jj]); A1[jj] = shift_down(A1[jj]); AE[jj] = shift_down(AE[jj]); AF[jj] = shift_down(AF[jj]);
@@ -677,18 +686,18 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             constexpr int U = decltype(u_tag)::value;
             if (U == 0) {
                 unsigned x = __shfl_up_sync(FULL, AE[P - 1], 1);             // neighbour's (E[P-1], E[C-1])
-                if (lane == 0) x = (unsigned)neg16 << 16;                    // left of k = -W: MINUS_INF2
+                if (lane == 0) x = (unsigned)(neg16 + BIAS16) << 16;         // left of k = -W: MINUS_INF2
                 const unsigned ein = prmt(x, AE[P - 1], 0x5432);             // lo: neighbour's E[C-1], hi: own E[P-1]
-                const unsigned best2 = step_cells16<C, 0>(A0, AE, AF, Qw, Rw, ein, p, mge2, mgoe2, floor2);
-                if (edge_lane) AE[JP] = JH ? ((AE[JP] & 0xffffu) | ((unsigned)FLOOR16 << 16)) : ((AE[JP] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu));
+                const unsigned best2 = step_cells16<C, 0>(A0, AE, AF, Qw, Rw, ein, p, mge2, mgoe32, floor2);
+                if (edge_lane) AE[JP] = JH ? ((AE[JP] & 0xffffu) | (FLOORU16 << 16)) : ((AE[JP] & 0xffff0000u) | FLOORU16);
                 shift_ref();
                 return scan_fast(best2, A0, dd, 0);
             } else {
                 unsigned y = __shfl_down_sync(FULL, AF[0], 1);               // neighbour's (F[0], F[P])
-                if (lane == 31) y = (unsigned)FLOOR16 & 0xffffu;             // right of the last lane: dead
+                if (lane == 31) y = FLOORU16;                                // right of the last lane: dead
                 const unsigned fin = prmt(AF[0], y, 0x5432);                 // lo: own F[P], hi: neighbour's F[0]
-                const unsigned best2 = step_cells16<C, 1>(A1, AE, AF, Qw, Rw, fin, p, mge2, mgoe2, floor2);
-                if (edge_lane) AF[JP] = JH ? ((AF[JP] & 0xffffu) | ((unsigned)neg16 << 16)) : ((AF[JP] & 0xffff0000u) | ((unsigned)neg16 & 0xffffu));
+                const unsigned best2 = step_cells16<C, 1>(A1, AE, AF, Qw, Rw, fin, p, mge2, mgoe32, floor2);
+                if (edge_lane) AF[JP] = JH ? ((AF[JP] & 0xffffu) | ((unsigned)(neg16 + BIAS16) << 16)) : ((AF[JP] & 0xffff0000u) | (unsigned)(neg16 + BIAS16));
                 shift_query();
                 return scan_fast(best2, A1, dd, 1);
             }
