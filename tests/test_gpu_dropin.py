@@ -81,3 +81,19 @@ def test_native_driver_and_runner_script_match_reference_outputs(tmp_path):
     assert len(open(out / "raw.log").read().split()) == 2
     tj = json.load(open(out / "time.json"))
     assert tj["AGAThA"]["test"] > 0
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(DROPIN)), reason="oracle/_ref binaries not built")
+def test_reference_driver_with_several_host_threads(tmp_path):
+    """-n 3: three OpenMP threads of the reference driver, each with its own pair of storages/streams (test_prog.cpp:210-245),
+    against the library's process-global state (scoring, launch configuration, stream cache). Batches finish in any order, so
+    the multiset of lines is compared."""
+    import agatha_b200 as ag
+    d = ag.synth_pairs(1, 21, 5000)
+    qf, tf = str(tmp_path / "q.fasta"), str(tmp_path / "t.fasta")
+    ag.write_fasta(qf, d["qbuf"], d["qoff"], d["qlen"])
+    ag.write_fasta(tf, d["tbuf"], d["toff"], d["tlen"])
+    ref_scores, _ = _run(REF, qf, tf, str(tmp_path), "ref1", extra=("-a", "512"))
+    new_scores, new_ms = _run(DROPIN, qf, tf, str(tmp_path), "new3", extra=("-n", "3", "-a", "512"))
+    assert sorted(new_scores.splitlines()) == sorted(ref_scores.splitlines())
+    assert len(new_ms) == 12          # 3 threads x ceil(1667/512) batches: one raw.log line per batch
