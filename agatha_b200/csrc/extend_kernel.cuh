@@ -358,8 +358,6 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     const int gl = 32 * warp + lane;                 // lane index inside the group: owns cells g in [C*gl, C*gl + C)
     static_assert((C % 8 == 0 || C == 2 || C == 4) && C <= 32, "cells per lane: 2, 4 or a multiple of 8");
     constexpr int NWORD = (C + 7) / 8;
-    using U0 = std::integral_constant<int, 0>;
-    using U1 = std::integral_constant<int, 1>;
     using M0 = std::integral_constant<int, 0>;
     using M1 = std::integral_constant<int, 1>;
     using M2 = std::integral_constant<int, 2>;
