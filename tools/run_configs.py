@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "configs_r01.json"))
     ap.add_argument("--pairs", type=int, default=100000)
     ap.add_argument("--only", default="")
+    ap.add_argument("--ref-pairs", type=int, default=0, help="override the size of the slice given to the reference GPU program")
     args = ap.parse_args()
     out = {}
     for name, prof, seed, n, W, nref in CONFIGS:
@@ -82,7 +83,7 @@ def main():
              "stops": {"end": int((res["stop"] == 0).sum()), "zdrop": int((res["stop"] == 1).sum()), "bandexit": int((res["stop"] == 2).sum())},
              "h2d_bytes": int(st["h2d_bytes"]), "batches": int(st["n_batches"])}
         # reference GPU program on a slice inside its int16 domain
-        ok = np.nonzero((d["qlen"] < 32768) & (d["tlen"] < 32768))[0][:nref]
+        ok = np.nonzero((d["qlen"] < 32768) & (d["tlen"] < 32768))[0][:(args.ref_pairs or nref)]
         sub = subset(d, ok)
         with tempfile.TemporaryDirectory() as tmp:
             ref_res, info = run_ref(sub, W, tmp)
