@@ -142,6 +142,27 @@ int agatha_pack_device(const uint8_t* d_query_bases, uint64_t query_bytes, const
     return AGATHA_OK;
 }
 
+int agatha_apply_ops_device(const uint8_t* d_query_bases, const uint8_t* d_target_bases,
+                            const uint32_t* d_query_offsets, const uint32_t* d_target_offsets,
+                            const uint32_t* d_query_lens, const uint32_t* d_target_lens,
+                            const uint8_t* d_query_ops, const uint8_t* d_target_ops, uint32_t n_alns,
+                            uint32_t* d_query_packed, uint32_t* d_target_packed, void* stream)
+{
+    if (n_alns == 0) return AGATHA_OK;
+    if (!d_query_bases || !d_target_bases || !d_query_offsets || !d_target_offsets || !d_query_lens || !d_target_lens ||
+        !d_query_ops || !d_target_ops || !d_query_packed || !d_target_packed) return set_error(AGATHA_EINVAL, "NULL argument");
+    if (agatha_device_count() == 0) return set_error(AGATHA_ENODEV, "no CUDA device");
+    uint64_t blocks = (2ull * n_alns + 7) / 8;                       // 8 warps per block, one warp per sequence
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    apply_ops_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_query_bases, d_target_bases, d_query_offsets, d_target_offsets,
+                                                                          d_query_lens, d_target_lens, d_query_ops, d_target_ops, n_alns,
+                                                                          d_query_packed, d_target_packed);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_error(e, "apply_ops_kernel launch");
+    return AGATHA_OK;
+}
+
 int agatha_extend_device(const uint32_t* d_query_packed, const uint32_t* d_target_packed,
                          const uint32_t* d_query_offsets, const uint32_t* d_target_offsets,
                          const uint32_t* d_query_lens, const uint32_t* d_target_lens,

@@ -200,6 +200,8 @@ void gasal_host_alns_resize(gasal_gpu_storage_t* g, int new_max_alns, Parameters
     if (agatha_stream_reserve(handle(g), (uint32_t)new_max_alns, 8, 8)) die("gasal_host_alns_resize");
     g->host_query_op = (uint8_t*)realloc(g->host_query_op, (size_t)new_max_alns);
     g->host_target_op = (uint8_t*)realloc(g->host_target_op, (size_t)new_max_alns);
+    memset(g->host_query_op + g->host_max_n_alns, 0, (size_t)new_max_alns - g->host_max_n_alns);
+    memset(g->host_target_op + g->host_max_n_alns, 0, (size_t)new_max_alns - g->host_max_n_alns);
     g->host_max_n_alns = (uint32_t)new_max_alns;
     refresh_views(g);
     fprintf(stderr, " done. This can harm performance.\n");
@@ -207,7 +209,7 @@ void gasal_host_alns_resize(gasal_gpu_storage_t* g, int new_max_alns, Parameters
 
 void gasal_op_fill(gasal_gpu_storage_t* g, uint8_t* data, uint32_t nbr_seqs_in_stream, data_source SRC)
 {
-    // reverse/complement ops are dead in the reference (isReverseComplement is never set, args_parser.cpp:28); kept for the API
+    // only applied when the caller sets params->isReverseComplement (the reference's driver never does, args_parser.cpp:28)
     uint8_t* dst = SRC == QUERY ? g->host_query_op : (SRC == TARGET ? g->host_target_op : nullptr);
     if (dst) memcpy(dst, data, nbr_seqs_in_stream);
 }
@@ -243,7 +245,13 @@ void gasal_aln_async(gasal_gpu_storage_t* g, const uint32_t actual_query_batch_b
         g_scores.slice_width = params->slice_width; g_scores.z_threshold = params->z_threshold; g_scores.band_width = params->band_width;
     }
     agatha_stream_t* s = handle(g);
-    if (agatha_stream_submit(s, actual_query_batch_bytes, actual_target_batch_bytes, actual_n_alns, &g_scores)) {
+    const bool with_ops = params && params->isReverseComplement;         // gasal_align.cu:199
+    if (with_ops && actual_n_alns <= g->host_max_n_alns) {
+        memcpy(agatha_stream_query_ops(s), g->host_query_op, actual_n_alns);
+        memcpy(agatha_stream_target_ops(s), g->host_target_op, actual_n_alns);
+    }
+    if (with_ops ? agatha_stream_submit_ops(s, actual_query_batch_bytes, actual_target_batch_bytes, actual_n_alns, &g_scores)
+                 : agatha_stream_submit(s, actual_query_batch_bytes, actual_target_batch_bytes, actual_n_alns, &g_scores)) {
         fprintf(stderr, "[GASAL ERROR:] %s\n", agatha_last_error());      // same checks/messages as gasal_align.cu:33-68
         exit(EXIT_FAILURE);
     }

@@ -60,6 +60,7 @@ struct JobView {
     const uint64_t *qo, *to;
     const uint32_t *ql, *tl;
     const agatha_params_t* params;
+    const uint8_t *qops, *tops;        // optional per-pair reverse/complement ops
     int32_t *score, *qend, *tend, *stop, *dstop;
 };
 
@@ -74,6 +75,10 @@ int fill_batch(Batch& b, const JobView& jv, int fill_threads, uint64_t& qbytes, 
     rc = agatha_stage_batch(jv.qb, jv.qo, jv.ql, b.ids.data(), n, agatha_stream_query_bases(b.s), qtot,
                             agatha_stream_query_offsets(b.s), agatha_stream_query_lens(b.s), &qbytes, fill_threads);
     if (rc) return rc;
+    if (jv.qops || jv.tops) {
+        uint8_t *qo = agatha_stream_query_ops(b.s), *to = agatha_stream_target_ops(b.s);
+        for (uint64_t j = 0; j < n; j++) { qo[j] = jv.qops ? jv.qops[b.ids[j]] : 0; to[j] = jv.tops ? jv.tops[b.ids[j]] : 0; }
+    }
     return agatha_stage_batch(jv.tb, jv.to, jv.tl, b.ids.data(), n, agatha_stream_target_bases(b.s), ttot,
                               agatha_stream_target_offsets(b.s), agatha_stream_target_lens(b.s), &tbytes, fill_threads);
 }
@@ -133,10 +138,11 @@ void run_worker(Worker& w, const JobView& jv, uint32_t batch_alns, int n_streams
         next += cnt;
         uint64_t qbytes = 0, tbytes = 0;
         int rc = fill_batch(b, jv, fill_threads, qbytes, tbytes);
-        if (!rc) rc = agatha_stream_submit(b.s, qbytes, tbytes, (uint32_t)cnt, jv.params);
+        if (!rc) rc = (jv.qops || jv.tops) ? agatha_stream_submit_ops(b.s, qbytes, tbytes, (uint32_t)cnt, jv.params)
+                                           : agatha_stream_submit(b.s, qbytes, tbytes, (uint32_t)cnt, jv.params);
         if (rc) { fail(rc); break; }
         b.busy = true;
-        w.h2d += qbytes + tbytes + 20ull * cnt;
+        w.h2d += qbytes + tbytes + 20ull * cnt + ((jv.qops || jv.tops) ? 2ull * cnt : 0);
         w.batches++;
         cur = (cur + 1) % n_streams;
     }
@@ -208,7 +214,8 @@ extern "C" int agatha_align_job(const uint8_t* query_bases, const uint64_t* quer
     }
     const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     const int fill_threads = (cfg && cfg->staging_threads > 0) ? cfg->staging_threads : std::max(1, std::min(8, hw / ndev));
-    JobView jv{query_bases, target_bases, query_offsets, target_offsets, query_lens, target_lens, params, score, query_end, target_end, stop, dstop};
+    JobView jv{query_bases, target_bases, query_offsets, target_offsets, query_lens, target_lens, params,
+               cfg ? cfg->query_ops : nullptr, cfg ? cfg->target_ops : nullptr, score, query_end, target_end, stop, dstop};
     std::vector<std::thread> threads;
     for (int i = 1; i < ndev; i++) threads.emplace_back(run_worker, std::ref(workers[(size_t)i]), std::cref(jv), batch_alns, n_streams, fill_threads);
     run_worker(workers[0], jv, batch_alns, n_streams, fill_threads);

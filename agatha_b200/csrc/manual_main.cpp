@@ -16,13 +16,13 @@
 
 static void usage()
 {
-    fprintf(stderr, "Usage: agatha_manual [-m] [-x] [-q] [-r] [-s] [-z] [-w] [-b] [-t] [-a] [-g] [-p] [-n] <query_batch.fasta> <target_batch.fasta> [raw_file]\n");
+    fprintf(stderr, "Usage: agatha_manual [-m] [-x] [-q] [-r] [-s] [-z] [-w] [-b] [-t] [-a] [-g] [-p] [-n] [-R] <query_batch.fasta> <target_batch.fasta> [raw_file]\n");
 }
 
 int main(int argc, char** argv)
 {
     agatha_params_t p = {2, 4, 4, 2, 3, 400, 751};   // args_parser.cpp:12-22
-    int print_out = 0, gpus = 0, batch = 0;
+    int print_out = 0, gpus = 0, batch = 0, apply_ops = 0;
     for (int c = 1; c < argc; c++) if (!strcmp(argv[c], "--help") || !strcmp(argv[c], "-h")) { usage(); return 0; }
     if (argc < 4) { fprintf(stderr, "Not enough Parameters. Required: file1.fasta file2.fasta. See help (--help, -h) for usage. \n"); return 1; }
     int c = 1;
@@ -42,6 +42,7 @@ int main(int argc, char** argv)
             case 'a': dst = &batch; break;
             case 'b': case 't': case 'n': dst = &dummy; break;
             case 'p': print_out = 1; break;
+            case 'R': apply_ops = 1; break;   // extension: honour the header characters '<' '/' '+' (test_prog.cpp:83-92)
             default: break;
         }
         if (dst) { c++; *dst = atoi(argv[c]); }
@@ -57,6 +58,7 @@ int main(int argc, char** argv)
     std::vector<int32_t> score(n), qend(n), tend(n);
     agatha_job_config_t cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.n_devices = gpus; cfg.batch_alns = batch > 0 ? (uint32_t)batch : 0u;
+    if (apply_ops) { cfg.query_ops = agatha_fasta_query_ops(f); cfg.target_ops = agatha_fasta_target_ops(f); }
     agatha_job_stats_t st;
     int rc = agatha_align_job(agatha_fasta_query_bases(f), agatha_fasta_query_offsets(f), agatha_fasta_query_lens(f),
                               agatha_fasta_target_bases(f), agatha_fasta_target_offsets(f), agatha_fasta_target_lens(f),

@@ -24,6 +24,7 @@ struct agatha_stream {
     uint64_t hcap_q = 0, hcap_t = 0;
     uint32_t* h_meta = nullptr;     // [qoff | toff | qlen | tlen | order] x cap_n
     int32_t* h_res = nullptr;       // [score | qend | tend | stop | dstop] x cap_n
+    uint8_t* h_ops = nullptr;       // [query op | target op] x cap_n, zero unless the caller fills them
     uint32_t cap_n = 0;
     // device
     uint8_t *d_q = nullptr, *d_t = nullptr;
@@ -31,6 +32,7 @@ struct agatha_stream {
     uint64_t dcap_q = 0, dcap_t = 0;
     uint32_t* d_meta = nullptr;
     int32_t* d_res = nullptr;
+    uint8_t* d_ops = nullptr;
     uint32_t dcap_n = 0;
     void* d_ws = nullptr;
     uint32_t cur_n = 0;
@@ -79,8 +81,8 @@ void agatha_stream_destroy(agatha_stream_t* s)
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->st) cudaStreamSynchronize(s->st);
-    cudaFreeHost(s->h_q); cudaFreeHost(s->h_t); cudaFreeHost(s->h_meta); cudaFreeHost(s->h_res);
-    cudaFree(s->d_q); cudaFree(s->d_t); cudaFree(s->d_qp); cudaFree(s->d_tp); cudaFree(s->d_meta); cudaFree(s->d_res); cudaFree(s->d_ws);
+    cudaFreeHost(s->h_q); cudaFreeHost(s->h_t); cudaFreeHost(s->h_meta); cudaFreeHost(s->h_res); cudaFreeHost(s->h_ops);
+    cudaFree(s->d_q); cudaFree(s->d_t); cudaFree(s->d_qp); cudaFree(s->d_tp); cudaFree(s->d_meta); cudaFree(s->d_res); cudaFree(s->d_ops); cudaFree(s->d_ws);
     for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
@@ -104,9 +106,10 @@ static int grow_device(agatha_stream_t* s, uint32_t n, uint64_t qbytes, uint64_t
     }
     if (n > s->dcap_n) {
         const uint32_t cap = std::max<uint32_t>(n, s->dcap_n * 2);
-        cudaFree(s->d_meta); cudaFree(s->d_res); s->d_meta = nullptr; s->d_res = nullptr; s->dcap_n = 0;
+        cudaFree(s->d_meta); cudaFree(s->d_res); cudaFree(s->d_ops); s->d_meta = nullptr; s->d_res = nullptr; s->d_ops = nullptr; s->dcap_n = 0;
         CK(cudaMalloc((void**)&s->d_meta, sizeof(uint32_t) * 5ull * cap), "cudaMalloc(meta)");
         CK(cudaMalloc((void**)&s->d_res, sizeof(int32_t) * 5ull * cap), "cudaMalloc(results)");
+        CK(cudaMalloc((void**)&s->d_ops, 2ull * cap), "cudaMalloc(ops)");
         s->dcap_n = cap;
     }
     return AGATHA_OK;
@@ -124,9 +127,15 @@ int agatha_stream_reserve(agatha_stream_t* s, uint32_t n_alns, uint64_t query_by
     if ((rc = grow_host_bases(&s->h_t, &s->hcap_t, round_up(target_bytes, 8), s->hcap_t))) return rc;
     if (n_alns > s->cap_n) {
         const uint32_t ncap = std::max<uint32_t>(n_alns, s->cap_n * 2);
-        uint32_t* nm = nullptr; int32_t* nr = nullptr;
+        uint32_t* nm = nullptr; int32_t* nr = nullptr; uint8_t* no = nullptr;
         CK(cudaHostAlloc((void**)&nm, sizeof(uint32_t) * 5ull * ncap, cudaHostAllocDefault), "cudaHostAlloc(meta)");
         CK(cudaHostAlloc((void**)&nr, sizeof(int32_t) * 5ull * ncap, cudaHostAllocDefault), "cudaHostAlloc(results)");
+        CK(cudaHostAlloc((void**)&no, 2ull * ncap, cudaHostAllocDefault), "cudaHostAlloc(ops)");
+        std::memset(no, 0, 2ull * ncap);
+        if (s->h_ops) {
+            for (int k = 0; k < 2; k++) std::memcpy(no + (size_t)k * ncap, s->h_ops + (size_t)k * s->cap_n, s->cap_n);
+            cudaFreeHost(s->h_ops);
+        }
         if (s->h_meta) {
             for (int k = 0; k < 5; k++) std::memcpy(nm + (size_t)k * ncap, s->h_meta + (size_t)k * s->cap_n, sizeof(uint32_t) * s->cap_n);
             cudaFreeHost(s->h_meta);
@@ -135,7 +144,7 @@ int agatha_stream_reserve(agatha_stream_t* s, uint32_t n_alns, uint64_t query_by
             for (int k = 0; k < 5; k++) std::memcpy(nr + (size_t)k * ncap, s->h_res + (size_t)k * s->cap_n, sizeof(int32_t) * s->cap_n);
             cudaFreeHost(s->h_res);
         }
-        s->h_meta = nm; s->h_res = nr; s->cap_n = ncap;
+        s->h_meta = nm; s->h_res = nr; s->h_ops = no; s->cap_n = ncap;
     }
     // device side too, so that a submit of anything that fits the reservation never allocates (cudaMalloc/cudaFree
     // synchronise the whole device)
@@ -154,8 +163,12 @@ uint32_t* agatha_stream_query_offsets(agatha_stream_t* s) { return s->h_meta; }
 uint32_t* agatha_stream_target_offsets(agatha_stream_t* s) { return s->h_meta + (size_t)s->cap_n; }
 uint32_t* agatha_stream_query_lens(agatha_stream_t* s) { return s->h_meta + 2 * (size_t)s->cap_n; }
 uint32_t* agatha_stream_target_lens(agatha_stream_t* s) { return s->h_meta + 3 * (size_t)s->cap_n; }
+uint8_t* agatha_stream_query_ops(agatha_stream_t* s) { return s->h_ops; }
+uint8_t* agatha_stream_target_ops(agatha_stream_t* s) { return s->h_ops + (size_t)s->cap_n; }
 
-int agatha_stream_submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns, const agatha_params_t* params)
+}  // extern "C"
+
+static int submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns, const agatha_params_t* params, bool with_ops)
 {
     if (!s) return set_error(AGATHA_EINVAL, "stream is NULL");
     // the reference's argument checks, gasal_align.cu:33-68
@@ -193,8 +206,14 @@ int agatha_stream_submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t targ
     for (int k = 0; k < 5; k++)
         CK(cudaMemcpyAsync(s->d_meta + (size_t)k * s->dcap_n, s->h_meta + (size_t)k * s->cap_n, sizeof(uint32_t) * n_alns, cudaMemcpyHostToDevice, st), "H2D batch metadata");
     if ((rc = agatha_pack_device(s->d_q, query_bytes, s->d_t, target_bytes, s->d_qp, s->d_tp, st))) return rc;
-    CK(cudaEventRecord(s->ev[1], st), "cudaEventRecord");
     const size_t dn = s->dcap_n;
+    if (with_ops) {                                   // gasal_align.cu:199-212
+        for (int k = 0; k < 2; k++)
+            CK(cudaMemcpyAsync(s->d_ops + (size_t)k * dn, s->h_ops + (size_t)k * s->cap_n, n_alns, cudaMemcpyHostToDevice, st), "H2D ops");
+        if ((rc = agatha_apply_ops_device(s->d_q, s->d_t, s->d_meta, s->d_meta + dn, s->d_meta + 2 * dn, s->d_meta + 3 * dn,
+                                          s->d_ops, s->d_ops + dn, n_alns, s->d_qp, s->d_tp, st))) return rc;
+    }
+    CK(cudaEventRecord(s->ev[1], st), "cudaEventRecord");
     rc = agatha_extend_device(s->d_qp, s->d_tp, s->d_meta, s->d_meta + dn, s->d_meta + 2 * dn, s->d_meta + 3 * dn, s->d_meta + 4 * dn,
                               n_alns, params, s->d_res, s->d_res + dn, s->d_res + 2 * dn, s->d_res + 3 * dn, s->d_res + 4 * dn, s->d_ws, st);
     if (rc) return rc;
@@ -205,6 +224,18 @@ int agatha_stream_submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t targ
     s->cur_n = n_alns;
     s->state = 1;
     return AGATHA_OK;
+}
+
+extern "C" {
+
+int agatha_stream_submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns, const agatha_params_t* params)
+{
+    return submit(s, query_bytes, target_bytes, n_alns, params, false);
+}
+
+int agatha_stream_submit_ops(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns, const agatha_params_t* params)
+{
+    return submit(s, query_bytes, target_bytes, n_alns, params, true);
 }
 
 static void finish(agatha_stream_t* s)

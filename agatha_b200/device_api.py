@@ -59,6 +59,15 @@ def pack_device(q_bases, t_bases, stream=None):
     return qp, tp
 
 
+def apply_ops_device(q_bases, t_bases, qoff, toff, qlen, tlen, qops, tops, qp, tp, stream=None):
+    """agatha_apply_ops_device: re-pack, in place in (qp, tp), the sequences whose op byte (uint8 CUDA tensors qops/tops;
+    bit 0 = reverse, bit 1 = complement) is non-zero. Call after pack_device on the same stream."""
+    torch = _torch()
+    st = stream if stream is not None else torch.cuda.current_stream(qp.device)
+    check(lib().agatha_apply_ops_device(_p(q_bases), _p(t_bases), _p(qoff), _p(toff), _p(qlen), _p(tlen), _p(qops), _p(tops),
+                                        ctypes.c_uint32(qlen.numel()), _p(qp), _p(tp), ctypes.c_void_p(st.cuda_stream)))
+
+
 def extend_device(qp, tp, qoff, toff, qlen, tlen, params, order=None, out=None, workspace=None, stream=None):
     """Launch the extension kernel on already packed, device-resident batches. All tensors int32 on CUDA
     (uint32 values); returns dict(score, query_end, target_end, stop, dstop) of int32 CUDA tensors."""
@@ -79,8 +88,9 @@ def extend_device(qp, tp, qoff, toff, qlen, tlen, params, order=None, out=None, 
     return out
 
 
-def align_pairs_device(pairs, params, device="cuda:0", bucket=True):
-    """Convenience for tests: stage -> H2D -> pack -> extend -> D2H. Returns a structured numpy array."""
+def align_pairs_device(pairs, params, device="cuda:0", bucket=True, ops=None):
+    """Convenience for tests: stage -> H2D -> pack [-> ops] -> extend -> D2H. Returns a structured numpy array.
+    ops: optional (query_ops, target_ops) uint8 arrays."""
     torch = _torch()
     qbuf, qoff, qlen, tbuf, toff, tlen = stage_pairs(pairs)
     dev = torch.device(device)
@@ -88,6 +98,9 @@ def align_pairs_device(pairs, params, device="cuda:0", bucket=True):
         tq = torch.from_numpy(qbuf).to(dev); tt = torch.from_numpy(tbuf).to(dev)
         qp, tp = pack_device(tq, tt)
         d = lambda a: torch.from_numpy(a.view(np.int32)).to(dev)
+        if ops is not None:
+            u8 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8)).to(dev)
+            apply_ops_device(tq, tt, d(qoff), d(toff), d(qlen), d(tlen), u8(ops[0]), u8(ops[1]), qp, tp)
         order = None
         if bucket:
             cost = np.minimum(qlen, tlen).astype(np.int64)

@@ -20,7 +20,7 @@ def _ptr(a, ty):
 
 class JobConfig(ctypes.Structure):
     _fields_ = [("n_devices", ctypes.c_int32), ("devices", i32p), ("batch_alns", ctypes.c_uint32), ("streams_per_device", ctypes.c_int32),
-                ("staging_threads", ctypes.c_int32)]
+                ("staging_threads", ctypes.c_int32), ("query_ops", u8p), ("target_ops", u8p)]
 
 
 class JobStats(ctypes.Structure):
@@ -107,17 +107,20 @@ def fasta_load(query_path, target_path):
     return out
 
 
-def write_fasta(path, buf, off, lens):
-    """Writes the reference's two-line '>>> idx' records (README.md:41-51)."""
+def write_fasta(path, buf, off, lens, ops=None):
+    """Writes the reference's two-line '>>> idx' records (README.md:41-51). ops (optional, 0..3 per record) selects the
+    first header character '>', '<', '/' or '+' = forward, reverse, complement, reverse-complement (test_prog.cpp:83-92)."""
     with open(path, "wb") as f:
         for i in range(len(lens)):
-            f.write(b">>> %d\n" % (i + 1))
+            f.write(b"%c>> %d\n" % (b"></+"[int(ops[i]) & 3] if ops is not None else b">"[0], i + 1))
             f.write(bytes(buf[int(off[i]):int(off[i]) + int(lens[i])]))
             f.write(b"\n")
 
 
-def align_job(qbuf, qoff, qlen, tbuf, toff, tlen, params, devices=None, n_devices=0, batch_alns=0, streams_per_device=0, staging_threads=0):
-    """agatha_align_job: pairs (unpadded ASCII, byte offsets) -> structured results in input order, plus stats dict."""
+def align_job(qbuf, qoff, qlen, tbuf, toff, tlen, params, devices=None, n_devices=0, batch_alns=0, streams_per_device=0, staging_threads=0,
+              query_ops=None, target_ops=None):
+    """agatha_align_job: pairs (unpadded ASCII, byte offsets) -> structured results in input order, plus stats dict.
+    query_ops / target_ops: optional per-pair op bytes (bit 0 = reverse, bit 1 = complement; test_prog.cpp:83-92)."""
     qbuf, tbuf = _a(qbuf, np.uint8), _a(tbuf, np.uint8)
     qoff, toff = _a(qoff, np.uint64), _a(toff, np.uint64)
     qlen, tlen = _a(qlen, np.uint32), _a(tlen, np.uint32)
@@ -131,6 +134,13 @@ def align_job(qbuf, qoff, qlen, tbuf, toff, tlen, params, devices=None, n_device
     else:
         cfg.n_devices = n_devices
     cfg.batch_alns = batch_alns; cfg.streams_per_device = streams_per_device; cfg.staging_threads = staging_threads
+    qops = tops = None
+    if query_ops is not None or target_ops is not None:
+        qops = _a(query_ops if query_ops is not None else np.zeros(n, np.uint8), np.uint8)
+        tops = _a(target_ops if target_ops is not None else np.zeros(n, np.uint8), np.uint8)
+        if len(qops) != n or len(tops) != n:
+            raise ValueError("ops must have one byte per pair")
+        cfg.query_ops = _ptr(qops, u8p); cfg.target_ops = _ptr(tops, u8p)
     res = {k: np.zeros(n, np.int32) for k in ("score", "query_end", "target_end", "stop", "dstop")}
     st = JobStats()
     check(lib().agatha_align_job(_ptr(qbuf, u8p), _ptr(qoff, u64p), _ptr(qlen, u32p), _ptr(tbuf, u8p), _ptr(toff, u64p), _ptr(tlen, u32p),
@@ -197,9 +207,15 @@ class Stream:
         self.n = n
         self.qbytes, self.tbytes = len(qbuf), len(tbuf)
 
-    def submit(self, params, qbytes=None, tbytes=None, n=None):
+    def set_ops(self, query_ops, target_ops):
+        """Per-sequence op bytes of the staged batch (gasal_op_fill, interfaces.cpp:69-84); used by submit(ops=True)."""
+        self._view("agatha_stream_query_ops", u8p, self.n)[:] = query_ops
+        self._view("agatha_stream_target_ops", u8p, self.n)[:] = target_ops
+
+    def submit(self, params, qbytes=None, tbytes=None, n=None, ops=False):
         p = params if isinstance(params, Params) else make_params(**params)
-        check(lib().agatha_stream_submit(self.h, ctypes.c_uint64(self.qbytes if qbytes is None else qbytes),
+        fn = lib().agatha_stream_submit_ops if ops else lib().agatha_stream_submit
+        check(fn(self.h, ctypes.c_uint64(self.qbytes if qbytes is None else qbytes),
                                          ctypes.c_uint64(self.tbytes if tbytes is None else tbytes),
                                          ctypes.c_uint32(self.n if n is None else n), ctypes.byref(p)))
 

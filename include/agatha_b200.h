@@ -74,6 +74,17 @@ int agatha_pack_device(const uint8_t *d_query_bases, uint64_t query_bytes,
                        const uint8_t *d_target_bases, uint64_t target_bytes,
                        uint32_t *d_query_packed, uint32_t *d_target_packed, void *stream);
 
+/* Per-sequence reverse / complement, GASAL2's "op" byte: bit 0 = reverse, bit 1 = complement (A<->T, C<->G on the 4-bit
+ * code). Replaces gasal_reversecomplement_kernel (kernels/pack_rc_seqs.h:56-212), which gasal_aln_async launches after
+ * packing when params->isReverseComplement is set (gasal_align.cu:199-212). Call it AFTER agatha_pack_device on the same
+ * stream, with the same ASCII batch: sequences whose op is non-zero are packed again with the operation applied to their
+ * real bases (the 'N' padding stays behind the sequence); sequences with op 0 are left alone. */
+int agatha_apply_ops_device(const uint8_t *d_query_bases, const uint8_t *d_target_bases,
+                            const uint32_t *d_query_offsets, const uint32_t *d_target_offsets,
+                            const uint32_t *d_query_lens, const uint32_t *d_target_lens,
+                            const uint8_t *d_query_ops, const uint8_t *d_target_ops, uint32_t n_alns,
+                            uint32_t *d_query_packed, uint32_t *d_target_packed, void *stream);
+
 /* The alignment itself. Replaces agatha_sort + host std::sort + agatha_kernel (gasal_align.cu:10-23,
  * kernels/agatha_kernel.h:49-458).
  *   d_*_offsets  start of each sequence in BASES (multiples of 8), as the reference's *_batch_offsets
@@ -117,11 +128,18 @@ uint32_t *agatha_stream_query_offsets(agatha_stream_t *s);
 uint32_t *agatha_stream_target_offsets(agatha_stream_t *s);
 uint32_t *agatha_stream_query_lens(agatha_stream_t *s);
 uint32_t *agatha_stream_target_lens(agatha_stream_t *s);
+/* Per-sequence op bytes (host_query_op / host_target_op, gasal.h:113-114; filled by gasal_op_fill, interfaces.cpp:69-84).
+ * Zero-initialised; only read by agatha_stream_submit_ops. */
+uint8_t *agatha_stream_query_ops(agatha_stream_t *s);
+uint8_t *agatha_stream_target_ops(agatha_stream_t *s);
 
 /* Asynchronous: H2D of the staged batch, pack, length-aware bucketing, extension kernel, D2H of the results.
  * query_bytes/target_bytes > 0 and multiples of 8, n_alns > 0 (gasal_align.cu:33-68). */
 int agatha_stream_submit(agatha_stream_t *s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns,
                          const agatha_params_t *params);
+/* Same, with the staged op bytes applied between packing and alignment (the reference's isReverseComplement path). */
+int agatha_stream_submit_ops(agatha_stream_t *s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns,
+                             const agatha_params_t *params);
 /* 0 = finished (results valid until the next submit), -1 = still running, -2 = nothing submitted
  * (the three return values of gasal_is_aln_async_done, gasal_align.cu:276-292). */
 int agatha_stream_poll(agatha_stream_t *s);
@@ -146,6 +164,8 @@ typedef struct {
     uint32_t batch_alns;      /* alignments per batch, 0 = default (8192) */
     int32_t streams_per_device; /* 0 = default (3) */
     int32_t staging_threads;  /* host threads per device that copy sequences into pinned staging, 0 = min(8, cores / devices) */
+    const uint8_t *query_ops; /* optional per-pair op bytes (bit 0 reverse, bit 1 complement); both NULL = no ops */
+    const uint8_t *target_ops;
 } agatha_job_config_t;
 
 typedef struct {

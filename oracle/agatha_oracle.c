@@ -259,3 +259,16 @@ int64_t agatha_oracle_band_cells(int32_t qlen, int32_t tlen, int32_t W)
     }
     return c;
 }
+
+/* pack_rc_seqs.h:111-169 (reverse) and :171-205 (complement) */
+void agatha_oracle_apply_op(uint8_t *seq, int32_t len, int32_t op)
+{
+    if (op & 1)
+        for (int32_t i = 0, j = len - 1; i < j; i++, j--) { uint8_t c = seq[i]; seq[i] = seq[j]; seq[j] = c; }
+    if (op & 2)
+        for (int32_t i = 0; i < len; i++) {
+            uint8_t lo = seq[i] & 15u;
+            lo = lo == 1 ? 4 : lo == 4 ? 1 : lo == 3 ? 7 : lo == 7 ? 3 : lo;
+            seq[i] = (uint8_t)((seq[i] & 0xF0u) | lo);
+        }
+}

@@ -61,6 +61,13 @@ int agatha_oracle_align_batch(const uint8_t *qbuf, const uint32_t *qoff, const u
 /* In-band real cells of the whole matrix (closed form of SURVEY.md section 8d), no stopping. */
 int64_t agatha_oracle_band_cells(int32_t qlen, int32_t tlen, int32_t band_width);
 
+/* Per-sequence reverse / complement op (bit 0 = reverse, bit 1 = complement), in place on the ASCII bases.
+ * Restates the intent of gasal_reversecomplement_kernel (kernels/pack_rc_seqs.h:56-212): reverse the real bases (the
+ * padding is not part of the sequence) and swap A<->T, C<->G by 4-bit code (low nibbles 1<->4, 3<->7), every other
+ * symbol unchanged. The high nibble of each byte is kept. See oracle/README.md for where the reference binary, as
+ * compiled with -DN_CODE=0x4E, departs from this for lengths that are not multiples of 8. */
+void agatha_oracle_apply_op(uint8_t *seq, int32_t len, int32_t op);
+
 /* Model switches for experiments (tests only). Bit 0: model phantom (padding) target columns
  * exactly like the reference (default on). */
 void agatha_oracle_set_model(int32_t flags);

@@ -96,6 +96,12 @@ class Oracle:
     def band_cells(self, qlen, tlen, w):
         return int(self.lib.agatha_oracle_band_cells(int(qlen), int(tlen), int(w)))
 
+    def apply_op(self, seq, op):
+        """Reverse (bit 0) / complement (bit 1) of one ASCII sequence; returns a new uint8 array."""
+        a = np.array(_as_u8(seq), dtype=np.uint8, copy=True)
+        self.lib.agatha_oracle_apply_op(_ptr(a, ctypes.c_uint8), ctypes.c_int32(len(a)), ctypes.c_int32(int(op)))
+        return a
+
 
 class RefHost:
     """The reference kernel itself, as host code. Valid only inside the reference's int16 domain."""

@@ -111,3 +111,19 @@ def test_batch_is_thread_count_invariant(oracle):
     a = oracle.align_pairs(pairs, p, nthreads=1)
     b = oracle.align_pairs(pairs, p, nthreads=4)
     assert (a == b).all()
+
+
+def test_apply_op_known_answers(oracle):
+    """Reverse / complement ops on the 4-bit code (kernels/pack_rc_seqs.h:111-205; header characters test_prog.cpp:83-92)."""
+    s = b"ACGTNacgtn"
+    assert bytes(oracle.apply_op(s, 0)) == s
+    assert bytes(oracle.apply_op(s, 1)) == s[::-1]
+    comp = bytes(oracle.apply_op(s, 2))
+    assert [c & 15 for c in comp] == [4, 7, 3, 1, 14, 4, 7, 3, 1, 14]          # T G C A N (by low nibble)
+    assert [c & 0xF0 for c in comp] == [c & 0xF0 for c in s]                   # high nibble (case) untouched
+    assert bytes(oracle.apply_op(s, 3)) == comp[::-1]
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 256, 1001).astype(np.uint8)
+    for k in range(4):
+        assert (oracle.apply_op(oracle.apply_op(x, k), k) == x).all()          # involutions
+    assert len(oracle.apply_op(b"", 3)) == 0
