@@ -362,6 +362,11 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     using M1 = std::integral_constant<int, 1>;
     using M2 = std::integral_constant<int, 2>;
     using M3 = std::integral_constant<int, 3>;
+    using M4 = std::integral_constant<int, 4>;
+    using S0 = std::integral_constant<int, 0>;
+    using S1 = std::integral_constant<int, 1>;
+    using S2 = std::integral_constant<int, 2>;
+    using S3 = std::integral_constant<int, 3>;
     using UA = std::integral_constant<int, WODD ? 1 : 0>;   // parity class of even anti-diagonals
     using UB = std::integral_constant<int, WODD ? 0 : 1>;   // ... of odd ones
     const int W = p.W;
@@ -420,6 +425,41 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         inject(-1, UB{});                           // u(-1) = (W-1) & 1
     }
 
+    // The same injection for a block of 8 prologue anti-diagonals d0 .. d0+7 with d0 % 8 == 0, when W % 8 == 7 (JWS >= 0)
+    // and C % 4 == 0. The two virtual cells move by one cell every second anti-diagonal, in opposite directions, and with
+    // this alignment their position INSIDE a group of four cells is a compile-time function of the step's place in the
+    // block (S = (d - d0) / 2 and its parity); only the group is a run-time value. A poke is then C/4 selects per array
+    // instead of C. blk_qt / blk_ql: index of the block's top / left group relative to this lane's first group (outside
+    // [0, C/4) = another lane's); blk_last: the block that ends at d = W.
+    //   top : g = (d+2+W)>>1 = G0 + S (even d), G0 + S + 1 (odd d),  G0 = (d0+W+1)/2 = 0 (mod 4)
+    //   left: g = (W-d-2)>>1 = GL0 - S (both parities),              GL0 = (W-3-d0)/2 = 2 (mod 4)
+    constexpr bool STATIC_PRO = JWS >= 0 && WODD && C % 4 == 0 && !GENERIC;
+    constexpr int NG = C / 4;
+    int blk_qt = 0, blk_ql = 0;
+    bool blk_last = false;
+    auto inject_static = [&](int d, auto u_tag, auto s_tag) {
+        constexpr int U = decltype(u_tag)::value, S = decltype(s_tag)::value;
+        constexpr bool EVEN = (U == UA::value);                            // the step on the even anti-diagonal of the pair
+        constexpr int PT = EVEN ? S : ((S + 1) & 3), PL = (2 - S) & 3;     // positions inside the group
+        const int hv = -(p.goe + p.ge * (d + 1)), gv = hv - p.goe;
+        const int qt = (!EVEN && S == 3) ? blk_qt + 1 : blk_qt;           // the odd step of S == 3 is already in the next group
+        const int ql = (S == 3) ? blk_ql - 1 : blk_ql;                    // ... and the left cell in the previous one
+        const bool h_top = !(EVEN && S == 3 && blk_last);                 // d + 2 > W: (0, d+2) does not exist, only F is needed
+#pragma unroll
+        for (int Q = 0; Q < NG; Q++) {
+            const bool ht = (qt == Q), hl = (ql == Q);
+            F[4 * Q + PT] = ht ? gv : F[4 * Q + PT];
+            E[4 * Q + PL] = hl ? gv : E[4 * Q + PL];
+            if (U == 0) {
+                H0[4 * Q + PT] = (ht && h_top) ? hv : H0[4 * Q + PT];
+                H0[4 * Q + PL] = hl ? hv : H0[4 * Q + PL];
+            } else {
+                H1[4 * Q + PT] = (ht && h_top) ? hv : H1[4 * Q + PT];
+                H1[4 * Q + PL] = hl ? hv : H1[4 * Q + PL];
+            }
+        }
+    };
+
     ScanState st = {0, 0, 0, scan_threshold(0, p)};   // agatha_kernel.h:158-161
     int stop = AGATHA_STOP_END, d_stop = pr.L;
     const bool has_phantom = pr.tcols > pr.tlen;
@@ -470,10 +510,11 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     // MODE 0 FAST: every in-band cell is inside the matrix. MODE 1 PRO: near edges only -- inject the boundary cells; what
     // lies beyond them is dead (NEGBIG), so the maximum needs no mask. MODE 2 TAIL: far edges only -- mask the maximum,
     // patch the padding columns. MODE 3: both (pairs shorter than the band).
-    auto do_step = [&](int d, bool scan, auto u_tag, auto mode_tag) -> bool {
+    // MODE 4: PRO inside an aligned block of 8 (inject_static; s_tag = place of the step's pair in the block).
+    auto do_step = [&](int d, bool scan, auto u_tag, auto mode_tag, auto s_tag) -> bool {
         constexpr int U = decltype(u_tag)::value;
         constexpr int MODE = decltype(mode_tag)::value;
-        constexpr bool FAST = MODE == 0, MASK = MODE >= 2, INJECT = MODE == 1 || MODE == 3;
+        constexpr bool FAST = MODE == 0, MASK = MODE == 2 || MODE == 3, INJECT = MODE == 1 || MODE == 3;
         using UN = std::integral_constant<int, 1 - U>;
         int jlo = 0, jhi = C - 1;
         if (MASK) {
@@ -507,6 +548,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             shift_query();
         }
         if (INJECT) { if (d < W) inject(d, u_tag); }
+        if (MODE == 4) { if (d < W) inject_static(d, u_tag, s_tag); }
         // padding columns enter the band only after d_tail, i.e. never right after a PRO step
         if (MASK) { if (has_phantom) phantom_patch(d + 1, UN{}); }    // inputs of the next anti-diagonal, before they are handed over
         if (NW == 1) {
@@ -727,6 +769,25 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         return 0;
     };
 
+    // aligned block of 8 prologue anti-diagonals, none of them near the far edges (slices are multiples of 8);
+    // returns 0, or 1 + the offset of the anti-diagonal on which Z-drop fired
+    auto pro_block = [&](int d) -> int {
+        if constexpr (STATIC_PRO) {
+            blk_qt = ((d + W + 1) >> 3) - NG * gl;
+            blk_ql = ((W + 1 - d) >> 3) - 1 - NG * gl;
+            blk_last = (d + 7 == W);
+            if (do_step(d,     true, UA{}, M4{}, S0{})) return 1;
+            if (do_step(d + 1, true, UB{}, M4{}, S0{})) return 2;
+            if (do_step(d + 2, true, UA{}, M4{}, S1{})) return 3;
+            if (do_step(d + 3, true, UB{}, M4{}, S1{})) return 4;
+            if (do_step(d + 4, true, UA{}, M4{}, S2{})) return 5;
+            if (do_step(d + 5, true, UB{}, M4{}, S2{})) return 6;
+            if (do_step(d + 6, true, UA{}, M4{}, S3{})) return 7;
+            if (do_step(d + 7, true, UB{}, M4{}, S3{})) return 8;
+        }
+        return 0;
+    };
+
     int d = 0;
     if (has_phantom) phantom_patch(0, UA{});
     if (NW > 1) {
@@ -769,18 +830,22 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 const int dlim = min(dend, d_fast_hi);
 #pragma unroll 1
                 for (; d < dlim; d += 2) {
-                    if (do_step(d, true, UA{}, M0{})) { fired = true; break; }
-                    if (do_step(d + 1, true, UB{}, M0{})) { fired = true; d++; break; }
+                    if (do_step(d, true, UA{}, M0{}, S0{})) { fired = true; break; }
+                    if (do_step(d + 1, true, UB{}, M0{}, S0{})) { fired = true; d++; break; }
                 }
                 if (fired) break;
+            } else if (STATIC_PRO && (d & 7) == 0 && d + 7 <= W && d + 7 < d_tail) {
+                const int off = pro_block(d);
+                if (off) { d += off - 1; fired = true; break; }
+                d += 8;
             } else {
                 if (has_phantom && d == d_fast_hi && d > 0) phantom_patch(d, UA{});   // first SLOW step after the FAST run
                 const bool s0 = wrap || d < pr.L, s1 = wrap || d + 1 < pr.L;
                 const bool far = d + 1 >= d_tail, near = d < W;                      // which matrix edges touch this pair of steps
                 bool f0, f1 = false;
-                if (!far)       { f0 = do_step(d, s0, UA{}, M1{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M1{}); }
-                else if (!near) { f0 = do_step(d, s0, UA{}, M2{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M2{}); }
-                else            { f0 = do_step(d, s0, UA{}, M3{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M3{}); }
+                if (!far)       { f0 = do_step(d, s0, UA{}, M1{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M1{}, S0{}); }
+                else if (!near) { f0 = do_step(d, s0, UA{}, M2{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M2{}, S0{}); }
+                else            { f0 = do_step(d, s0, UA{}, M3{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M3{}, S0{}); }
                 if (f0) { fired = true; break; }
                 if (f1) { fired = true; d++; break; }
                 d += 2;
