@@ -97,6 +97,15 @@ int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
     const char* env = getenv("AGATHA_S16");
     kp->s16 = (!kp->force_generic && p->match >= 0 && p->match <= 100 && p->mismatch <= 100 && p->gap_open >= 0 && p->gap_extend >= 0 &&
                p->gap_open + 2 * p->gap_extend <= 2000 && !(env && env[0] == '0')) ? 1 : 0;
+    // bit 1: the prologue (anti-diagonals 0..W) may run packed too, without a range monitor. On those anti-diagonals every
+    // live value lies in [-(2*goe + ge*(W+1)) - mismatch*(W+2)/2 - goe, match*(W+2)/2] (a cell is at most (W+2)/2 diagonal
+    // steps away from a matrix-edge value) and a dead cell creeps up by at most match*(W+2)/2 from the floor (-30000):
+    // both must stay well apart and inside 16 bits.
+    if (kp->s16) {
+        const long long half = (p->band_width + 2) / 2;
+        const long long depth = 3LL * kp->goe + (long long)kp->ge * (p->band_width + 1) + (long long)(p->mismatch + p->match) * half + 256;
+        if (depth < 24000 && !(env && env[0] == '1' && env[1] == '\0')) kp->s16 |= 2;
+    }
     return AGATHA_OK;
 }
 

@@ -721,12 +721,19 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             const int jb = __shfl_sync(FULL, search(A, ev_hrel), src);
             return scan_update(st, ev_hrel + base, C * src + jb, dd, u, p);
         };
-        // one packed anti-diagonal; true = scan_slow must look at it
-        auto step16 = [&](int dd, auto u_tag) -> bool {
+        // one packed anti-diagonal; true = scan_slow must look at it. PRO: an anti-diagonal of the prologue (d <= W): what
+        // lies beyond the matrix edges is dead, the caller injects the edge cells after the scan.
+        auto step16 = [&](int dd, auto u_tag, auto pro_tag) -> bool {
             constexpr int U = decltype(u_tag)::value;
+            constexpr bool PRO = decltype(pro_tag)::value != 0;
             if (U == 0) {
                 unsigned x = __shfl_up_sync(FULL, AE[P - 1], 1);             // neighbour's (E[P-1], E[C-1])
-                if (lane == 0) x = (unsigned)(neg16 + BIAS16) << 16;         // left of k = -W: MINUS_INF2
+                if (lane == 0) {
+                    // left of k = -W: MINUS_INF2; in the prologue the cell is not real yet (dead), and on d == W its left
+                    // neighbour is the matrix-edge value E(W,0) (agatha_kernel.h:130), exactly as in do_step
+                    if (!PRO) x = (unsigned)(neg16 + BIAS16) << 16;
+                    else x = (unsigned)(((dd == W) ? (-(p.goe + p.ge * W) - p.goe - base) : FLOOR16) + BIAS16) << 16;
+                }
                 const unsigned ein = prmt(x, AE[P - 1], 0x5432);             // lo: neighbour's E[C-1], hi: own E[P-1]
                 const unsigned best2 = step_cells16<C, 0>(A0, AE, AF, Qw, Rw, ein, p, mge2, mgoe32, floor2);
                 if (edge_lane) AE[JP] = JH ? ((AE[JP] & 0xffffu) | (FLOORU16 << 16)) : ((AE[JP] & 0xffff0000u) | FLOORU16);
@@ -737,11 +744,106 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 if (lane == 31) y = FLOORU16;                                // right of the last lane: dead
                 const unsigned fin = prmt(AF[0], y, 0x5432);                 // lo: own F[P], hi: neighbour's F[0]
                 const unsigned best2 = step_cells16<C, 1>(A1, AE, AF, Qw, Rw, fin, p, mge2, mgoe32, floor2);
-                if (edge_lane) AF[JP] = JH ? ((AF[JP] & 0xffffu) | ((unsigned)(neg16 + BIAS16) << 16)) : ((AF[JP] & 0xffff0000u) | (unsigned)(neg16 + BIAS16));
+                // k = +W reads MINUS_INF2 from outside the band; in the prologue that cell is dead until F(0,W) is injected
+                if (!PRO) { if (edge_lane) AF[JP] = JH ? ((AF[JP] & 0xffffu) | ((unsigned)(neg16 + BIAS16) << 16)) : ((AF[JP] & 0xffff0000u) | (unsigned)(neg16 + BIAS16)); }
                 shift_query();
                 return scan_fast(best2, A1, dd, 1);
             }
         };
+        // inject_static on the packed arrays: cell j = 4Q + pos lives in register (4Q + pos) % P, half Q / (NG/2); the value
+        // is dropped into that half with a PRMT whose selector is chosen per candidate register
+        // Selectors for the block: keep / replace the low half / replace the high half of candidate register 4R + pos, for the
+        // block's top group, the group after it, the left group and the group before it. Computed once per block.
+        constexpr int NGH = NG / 2, NSEL = NGH > 0 ? NGH : 1;
+        unsigned selT[NSEL], selTn[NSEL], selL[NSEL], selLp[NSEL];
+        auto block_selectors = [&]() {
+#pragma unroll
+            for (int R = 0; R < NGH; R++) {
+                auto pick = [&](int q) { return (q == R) ? 0x3254u : ((q == R + NGH) ? 0x7610u : 0x3210u); };
+                selT[R] = pick(blk_qt); selTn[R] = pick(blk_qt + 1);
+                selL[R] = pick(blk_ql); selLp[R] = pick(blk_ql - 1);
+            }
+        };
+        auto inject16 = [&](int dd, auto u_tag, auto s_tag) {
+            constexpr int U = decltype(u_tag)::value, S = decltype(s_tag)::value;
+            constexpr bool EVEN = (U == UA::value);
+            constexpr int PT = EVEN ? S : ((S + 1) & 3), PL = (2 - S) & 3;
+            const int hv = -(p.goe + p.ge * (dd + 1)) - base, gv = hv - p.goe;
+            const unsigned hv2 = pack16(hv, hv), gv2 = pack16(gv, gv);
+            const bool h_top = !(EVEN && S == 3 && blk_last);                 // d + 2 > W: only F is needed
+#pragma unroll
+            for (int R = 0; R < NGH; R++) {
+                const unsigned st_ = (!EVEN && S == 3) ? selTn[R] : selT[R];  // the odd step of S == 3 is already in the next group
+                const unsigned sl_ = (S == 3) ? selLp[R] : selL[R];           // ... and the left cell in the previous one
+                const unsigned sh_ = h_top ? st_ : 0x3210u;
+                AF[4 * R + PT] = prmt(AF[4 * R + PT], gv2, st_);
+                AE[4 * R + PL] = prmt(AE[4 * R + PL], gv2, sl_);
+                if (U == 0) { A0[4 * R + PT] = prmt(A0[4 * R + PT], hv2, sh_); A0[4 * R + PL] = prmt(A0[4 * R + PL], hv2, sl_); }
+                else        { A1[4 * R + PT] = prmt(A1[4 * R + PT], hv2, sh_); A1[4 * R + PL] = prmt(A1[4 * R + PL], hv2, sl_); }
+            }
+        };
+        // One aligned block of 8 prologue anti-diagonals as straight-line code with re-entry points: a step whose
+        // anti-diagonal might fire Z-drop leaves the block (returns 1 + 2*offset); the caller looks at it outside of the hot
+        // code (scan_slow: two searches, ~300 instructions) and comes back through `entry` to the injection that follows that
+        // step. Keeping the cold code out of the block matters: at 8 x ~200 instructions the block just fits the 32 KB
+        // instruction cache, with the scan inlined eight times it did not (ncu: 3 of 4 issue slots lost to instruction fetch).
+        // The scan -- including the search for the position of a low maximum -- runs BEFORE the injection, so an injected
+        // edge value can never be mistaken for the anti-diagonal's maximum.
+        using PRO1 = std::integral_constant<int, 1>;
+        using PRO0 = std::integral_constant<int, 0>;
+        auto pro_block16 = [&](int d0, int entry) -> int {
+            switch (entry) {
+            case 0:  if (step16(d0, UA{}, PRO1{})) return 1;
+            [[fallthrough]];
+            case 1:  inject16(d0, UA{}, S0{});
+                     if (step16(d0 + 1, UB{}, PRO1{})) return 3;
+            [[fallthrough]];
+            case 3:  inject16(d0 + 1, UB{}, S0{});
+                     if (step16(d0 + 2, UA{}, PRO1{})) return 5;
+            [[fallthrough]];
+            case 5:  inject16(d0 + 2, UA{}, S1{});
+                     if (step16(d0 + 3, UB{}, PRO1{})) return 7;
+            [[fallthrough]];
+            case 7:  inject16(d0 + 3, UB{}, S1{});
+                     if (step16(d0 + 4, UA{}, PRO1{})) return 9;
+            [[fallthrough]];
+            case 9:  inject16(d0 + 4, UA{}, S2{});
+                     if (step16(d0 + 5, UB{}, PRO1{})) return 11;
+            [[fallthrough]];
+            case 11: inject16(d0 + 5, UB{}, S2{});
+                     if (step16(d0 + 6, UA{}, PRO1{})) return 13;
+            [[fallthrough]];
+            case 13: inject16(d0 + 6, UA{}, S3{});                          // d0 + 6 <= W - 1: always an injection
+                     if (step16(d0 + 7, UB{}, PRO1{})) return 15;
+            [[fallthrough]];
+            default: if (d0 + 7 < W) inject16(d0 + 7, UB{}, S3{});          // nothing after the anti-diagonal d == W
+            }
+            return 0;
+        };
+        if (d == 0) {
+            // the whole prologue in aligned blocks of 8 (the caller guarantees STATIC_PRO, p.s16 & 2 and W + 1 < d_tail). Inside
+            // it no value can leave the 16-bit range (host-side bound, engine.cu), so there is no range check and no bail-out.
+            int entry = 0;
+            for (;;) {
+                int ev = 0;
+#pragma unroll 1
+                for (; d + 7 <= W; d += 8) {
+                    blk_qt = ((d + W + 1) >> 3) - NG * gl;
+                    blk_ql = ((W + 1 - d) >> 3) - 1 - NG * gl;
+                    blk_last = (d + 7 == W);
+                    block_selectors();
+                    ev = pro_block16(d, entry);
+                    entry = 0;
+                    if (ev) break;
+                }
+                if (!ev) break;
+                const int o = ev >> 1;                                       // the anti-diagonal d + o needs a closer look
+                const bool u1 = ((o & 1) == 0) == WODD;                      // even offsets are UA steps: parity class 1 iff W is odd
+                if (u1 ? scan_slow(A1, d + o, 1) : scan_slow(A0, d + o, 0)) { resolve(); d += o; return 1; }
+                entry = ev;                                                  // back into the same block, at the injection after that step
+            }
+            if (!check_range()) { resolve(); unpack(); return 2; }
+        } else
         if (!check_range()) return 2;                                        // 32-bit arrays untouched so far
         for (;;) {
             // hot loop: up to 32 anti-diagonals between two range checks, left early only for a possible Z-drop
@@ -749,12 +851,12 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             int ev = 0;
 #pragma unroll 1
             for (; d < dchunk; d += 2) {
-                if (step16(d, UA{})) { ev = 1; break; }
-                if (step16(d + 1, UB{})) { ev = 2; break; }
+                if (step16(d, UA{}, PRO0{})) { ev = 1; break; }
+                if (step16(d + 1, UB{}, PRO0{})) { ev = 2; break; }
             }
             if (ev == 1) {
                 if (WODD ? scan_slow(A1, d, 1) : scan_slow(A0, d, 0)) { resolve(); return 1; }
-                if (step16(d + 1, UB{})) ev = 2;                             // finish the pair (cold copy of the second step)
+                if (step16(d + 1, UB{}, PRO0{})) ev = 2;                             // finish the pair (cold copy of the second step)
                 else d += 2;
             }
             if (ev == 2) {
@@ -819,7 +921,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         }
         bool fired = false, reslice = false;
         while (d < dend) {
-            if (d >= d_fast_lo && d < d_fast_hi) {
+            if ((d >= d_fast_lo && d < d_fast_hi) || (CAN16 && STATIC_PRO && d == 0 && allow16 && (p.s16 & 2) && d_fast_lo < d_fast_hi)) {
                 if (CAN16 && allow16) {
                     const int rc = run_fast16(d);          // may cross slice boundaries: re-derive the slice afterwards
                     if (rc == 1) { fired = true; break; }

@@ -95,3 +95,42 @@ def test_off_band_repeat_does_not_leak_into_the_band(oracle):
             exp = oracle.align_pairs([(q, t)], op.make_params(**pkw))
             for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
                 assert got[a][0] == exp[b][0], (pkw, a, got, exp)
+
+
+@pytest.mark.parametrize("w", [63, 255, 751, 1023, 4095])
+def test_zdrop_and_band_shifts_inside_the_prologue(oracle, w, monkeypatch):
+    """The first W+1 anti-diagonals run in aligned blocks of 8 with the matrix-edge cells injected at compile-time positions
+    (packed 16-bit state for one-warp shapes, 32-bit for the wide ones). Z-drop must be able to fire on every place of a
+    block, a low anti-diagonal that does NOT fire (the best cell moved off the diagonal, so l*ge raises the bar) must leave
+    the block and come back, and all of it must match the oracle and the plain 32-bit path."""
+    import agatha_b200 as ag
+    rng = np.random.default_rng(w)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seq = lambda n: acgt[rng.integers(0, 4, int(n))]
+    L = 3 * w + 600
+    pairs = []
+    for cut in list(range(0, 40)) + [int(x) for x in rng.integers(40, max(41, w // 2 + 20), 60)]:
+        t = seq(L)
+        pairs.append((np.concatenate([t[:cut], seq(L - cut)]), t))                 # junk after `cut` matching bases
+    for _ in range(40):                                                            # a long gap early: the best cell leaves the diagonal
+        t = seq(L)
+        a, gap = int(rng.integers(5, max(6, w // 3))), int(rng.integers(10, max(11, w // 2)))
+        q = np.concatenate([t[:a], t[a + gap:]]) if rng.random() < 0.5 else np.concatenate([t[:a], seq(gap), t[a:]])
+        b = int(rng.integers(a + 5, a + 5 + w // 2))
+        pairs.append((np.concatenate([q[:b], seq(max(L - b, 1))]), t))
+    for pkw in (dict(z_threshold=20), dict(z_threshold=100, gap_extend=2), dict(z_threshold=400), dict(z_threshold=60, match=2, mismatch=6, gap_open=3, gap_extend=1),
+                dict(z_threshold=-1)):
+        pkw = dict(pkw, band_width=w)
+        exp = oracle.align_pairs(pairs, op.make_params(**pkw))
+        res = {}
+        for mode in ("2", "1", "0"):                                               # packed prologue / packed steady state only / 32-bit
+            monkeypatch.setenv("AGATHA_S16", mode)
+            res[mode] = ag.align_pairs_device(pairs, ag.make_params(**pkw))
+        for mode, got in res.items():
+            for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
+                bad = np.nonzero(got[a] != exp[b])[0]
+                assert len(bad) == 0, f"AGATHA_S16={mode} {pkw}: {len(bad)} pairs differ in {a}, first {bad[0]}: gpu {got[bad[0]]} oracle {exp[bad[0]]}"
+        if w <= 1023:
+            ds = exp["d_stop"][exp["stop"] == 1]
+            if pkw["z_threshold"] == 20:
+                assert len(set(int(x) % 8 for x in ds if x <= w)) == 8             # fired on every place of a block
