@@ -90,10 +90,10 @@ int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
     const unsigned m = (unsigned)p->match & 0xffu, x = (unsigned)(-p->mismatch) & 0xffu;
     kp->tab_lo = m | (x << 8) | (x << 16) | (x << 24);
     kp->tab_hi = 0xffffffffu;
-    kp->one = 1; kp->k32 = 32;
+    kp->one = 1; kp->k32 = 32; kp->m16 = 0xffff;
     kp->force_generic = fast_table_ok(p) ? 0 : 1;
     // 16-bit packed steady state (extend_kernel.cuh run_fast16): needs small scoring values so that the per-window drift
-    // bounds of its range monitor hold; AGATHA_S16=0 disables it (A/B measurements)
+    // bounds of its range monitor hold; AGATHA_S16=0 disables it, 1 = steady state only, 7 = also the tail (A/B measurements)
     const char* env = getenv("AGATHA_S16");
     kp->s16 = (!kp->force_generic && p->match >= 0 && p->match <= 100 && p->mismatch <= 100 && p->gap_open >= 0 && p->gap_extend >= 0 &&
                p->gap_open + 2 * p->gap_extend <= 2000 && !(env && env[0] == '0')) ? 1 : 0;
@@ -104,7 +104,12 @@ int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
     if (kp->s16) {
         const long long half = (p->band_width + 2) / 2;
         const long long depth = 3LL * kp->goe + (long long)kp->ge * (p->band_width + 1) + (long long)(p->mismatch + p->match) * half + 256;
-        if (depth < 24000 && !(env && env[0] == '1' && env[1] == '\0')) kp->s16 |= 2;
+        const bool only_steady = env && env[0] == '1' && env[1] == '\0', with_tail = env && env[0] == '7' && env[1] == '\0';
+        if (depth < 24000 && !only_steady) kp->s16 |= 2;
+        // bit 2: the tail (far matrix edges) packed as well (it keeps the range monitor, so it needs no bound of its own).
+        // Opt-in (AGATHA_S16=7): bit-exact and 12-14 % faster on equal-length pairs, but on mixed-length batches the extra
+        // loop costs more in instruction fetch than it saves in issue slots (C1: 21.2 -> 27.0 ms, ncu: no_instruction 1.6 -> 2.9).
+        if (with_tail) kp->s16 |= 4;
     }
     return AGATHA_OK;
 }

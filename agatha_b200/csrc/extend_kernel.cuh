@@ -41,7 +41,8 @@ struct KernelParams {
     unsigned tab_lo, tab_hi;         // PRMT lookup table: byte x -> score for code XOR x (fast alphabet)
     int LW, JW;                      // lane / cell index of k = +W  (global cell index g = W, u = 0)
     int one, k32;                    // the constants 1 and 32, opaque to ptxas: keep a*1+c and h*32+j on IMAD (FMA pipe)
-    int s16;                         // steady state may run on 16-bit packed state (scoring small enough, see engine.cu)
+    int m16;                         // 0xffff, opaque too: (bit pair) * 0xffff widens a valid-cell bit to a 16-bit mask on the FMA pipe
+    int s16;                         // bit 0: steady state, bit 1: prologue, bit 2: tail may run on 16-bit packed state (engine.cu)
     int force_generic;               // match/mismatch do not fit the byte table: score every pair with compare/select
 };
 
@@ -159,10 +160,14 @@ __device__ __forceinline__ unsigned pack16raw(int lo, int hi) { return ((unsigne
 __device__ __forceinline__ int lo16(unsigned x) { return (int)(x & 0xffffu) - BIAS16; }
 __device__ __forceinline__ int hi16(unsigned x) { return (int)(x >> 16) - BIAS16; }
 
-template <int C, int U>
+// TAILM: `vm2` holds one bit per cell of this anti-diagonal that lies inside the matrix (cells 0..P-1 in bits 0.., cells
+// P..C-1 in bits 16..); the others still take part in the recurrence (nothing inside the matrix ever reads them) but are
+// kept out of the maximum: their halves are ANDed to 0, the smallest packed value.
+template <int C, int U, bool TAILM = false>
 __device__ __forceinline__ unsigned step_cells16(unsigned (&H)[C / 2], unsigned (&E)[C / 2], unsigned (&F)[C / 2],
                                                  const uint32_t (&Qw)[(C + 7) / 8], const uint32_t (&Rw)[(C + 7) / 8],
-                                                 unsigned edge_in, const KernelParams& p, unsigned mge2, int mgoe32, unsigned floor2)
+                                                 unsigned edge_in, const KernelParams& p, unsigned mge2, int mgoe32, unsigned floor2,
+                                                 unsigned vm2 = 0u)
 {
     constexpr int P = C / 2, NWORD = (C + 7) / 8;
     unsigned sc[2 * NWORD];
@@ -189,7 +194,9 @@ __device__ __forceinline__ unsigned step_cells16(unsigned (&H)[C / 2], unsigned 
         E[jj] = __viaddmax_u16x2(ein, mge2, t);
         F[jj] = __viaddmax_u16x2(fin, mge2, t);
         H[jj] = h;
-        if (t_ & 1) best = __vimax3_u16x2(best, pend, h); else pend = h;
+        unsigned hm = h;
+        if (TAILM) hm = h & (unsigned)imad((int)((vm2 >> jj) & 0x00010001u), p.m16, 0);
+        if (t_ & 1) best = __vimax3_u16x2(best, pend, hm); else pend = hm;
     }
     if (P & 1) best = __vimax3_u16x2(best, pend, pend);
     return best;
@@ -460,6 +467,18 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         }
     };
 
+    // The step's place in its block selects one of four small bodies through a warp-uniform switch: the loop stays two
+    // anti-diagonals long (small enough for the instruction cache) and still pokes compile-time positions.
+    int blk_S = 0;
+    auto inject_static_sw = [&](int d, auto u_tag) {
+        switch (blk_S) {
+        case 0: inject_static(d, u_tag, S0{}); break;
+        case 1: inject_static(d, u_tag, S1{}); break;
+        case 2: inject_static(d, u_tag, S2{}); break;
+        default: inject_static(d, u_tag, S3{}); break;
+        }
+    };
+
     ScanState st = {0, 0, 0, scan_threshold(0, p)};   // agatha_kernel.h:158-161
     int stop = AGATHA_STOP_END, d_stop = pr.L;
     const bool has_phantom = pr.tcols > pr.tlen;
@@ -510,7 +529,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     // MODE 0 FAST: every in-band cell is inside the matrix. MODE 1 PRO: near edges only -- inject the boundary cells; what
     // lies beyond them is dead (NEGBIG), so the maximum needs no mask. MODE 2 TAIL: far edges only -- mask the maximum,
     // patch the padding columns. MODE 3: both (pairs shorter than the band).
-    // MODE 4: PRO inside an aligned block of 8 (inject_static; s_tag = place of the step's pair in the block).
+    // MODE 4: PRO with inject_static (blk_* describe the aligned block of 8 the step belongs to).
     auto do_step = [&](int d, bool scan, auto u_tag, auto mode_tag, auto s_tag) -> bool {
         constexpr int U = decltype(u_tag)::value;
         constexpr int MODE = decltype(mode_tag)::value;
@@ -548,7 +567,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             shift_query();
         }
         if (INJECT) { if (d < W) inject(d, u_tag); }
-        if (MODE == 4) { if (d < W) inject_static(d, u_tag, s_tag); }
+        if (MODE == 4) { if (d < W) inject_static_sw(d, u_tag); }
         // padding columns enter the band only after d_tail, i.e. never right after a PRO step
         if (MASK) { if (has_phantom) phantom_patch(d + 1, UN{}); }    // inputs of the next anti-diagonal, before they are handed over
         if (NW == 1) {
@@ -698,14 +717,18 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         // the hot loop only carries the common cases. scan_fast: nothing to do, or a new maximum (snapshot for the lazy
         // argmax); returns true when the anti-diagonal might fire Z-drop -> scan_slow, outside the hot loop.
         int ev_lane_h = 0, ev_hrel = 0;
-        auto scan_fast = [&](unsigned best2, const unsigned (&A)[P], int dd, int u) -> bool {
+        // tail: valid-cell bits of the anti-diagonal being computed (layout as in step_cells16) and the matching 16-bit masks
+        unsigned vm2 = 0u;
+        bool in_tail = false;
+        auto half_mask = [&](int jj) -> unsigned { return (unsigned)imad((int)((vm2 >> jj) & 0x00010001u), p.m16, 0); };
+        auto scan_fast = [&](unsigned best2, const unsigned (&A)[P], int dd, int u, bool TAILM) -> bool {   // TAILM is a constant at every call site (a generic lambda here crashes cicc 12.9)
             const int lane_h = max(lo16(best2), hi16(best2));
             const int hrel = __reduce_max_sync(FULL, lane_h);
             if (hrel <= maxrel && hrel >= thrrel) return false;
             if (hrel > maxrel) {
                 const unsigned who = __ballot_sync(FULL, lane_h == hrel);
 #pragma unroll
-                for (int jj = 0; jj < P; jj++) S[jj] = A[jj];
+                for (int jj = 0; jj < P; jj++) S[jj] = TAILM ? (A[jj] & half_mask(jj)) : A[jj];   // cells outside the matrix never match
                 snap_d = dd; snap_u = u; snap_src = 31 - __clz((int)who); snap_h = hrel;   // ties -> largest target index
                 st.max = hrel + base; st.thr = scan_threshold(st.max, p);
                 maxrel = hrel; thrrel = rel_thr();
@@ -718,14 +741,55 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             resolve();                                                       // the test needs (mt, mq)
             const unsigned who = __ballot_sync(FULL, ev_lane_h == ev_hrel);
             const int src = 31 - __clz((int)who);
-            const int jb = __shfl_sync(FULL, search(A, ev_hrel), src);
+            unsigned B[P];
+#pragma unroll
+            for (int jj = 0; jj < P; jj++) B[jj] = in_tail ? (A[jj] & half_mask(jj)) : A[jj];
+            const int jb = __shfl_sync(FULL, search(B, ev_hrel), src);
             return scan_update(st, ev_hrel + base, C * src + jb, dd, u, p);
+        };
+        // phantom_patch on the packed arrays (tail only; rare: a padding column at the first row of a slice chunk). Run-time
+        // cell index -> compare + select of a PRMT selector per register; j < 0 (another lane's cell) changes nothing.
+        auto poke16 = [&](unsigned (&A)[P], int j, unsigned v2) {
+#pragma unroll
+            for (int jj = 0; jj < P; jj++) {
+                const unsigned sel = (j == jj) ? 0x3254u : ((j == jj + P) ? 0x7610u : 0x3210u);
+                A[jj] = prmt(A[jj], v2, sel);
+            }
+        };
+        auto phantom_patch16 = [&](int dn, auto u_tag) {
+            constexpr int U = decltype(u_tag)::value;
+            const int qc = (dn - pr.tlen) & ~7;
+            if (dn - pr.tlen < 0 || dn - qc >= pr.tcols || qc >= pr.qlen) return;
+            if (!(qc == 0 || ((qc >> 3) + pr.pt - 1) % p.sw == 0)) return;
+            const int r = dn - qc, k = r - qc;
+            if (k > W || k < -W) return;
+            const unsigned v2 = pack16(neg16, neg16);
+            const int g = (k + W - U) >> 1;
+            const int gf = (U == 0) ? g : g + 1;
+            const int jf = gf - C * gl;
+            poke16(AF, (jf >= 0 && jf < C) ? jf : -1, v2);
+            if (r - 1 >= pr.tlen) {
+                const int j = g - C * gl;
+                const int jj = (j >= 0 && j < C) ? j : -1;
+                if (U == 0) poke16(A0, jj, v2); else poke16(A1, jj, v2);
+            }
         };
         // one packed anti-diagonal; true = scan_slow must look at it. PRO: an anti-diagonal of the prologue (d <= W): what
         // lies beyond the matrix edges is dead, the caller injects the edge cells after the scan.
         auto step16 = [&](int dd, auto u_tag, auto pro_tag) -> bool {
             constexpr int U = decltype(u_tag)::value;
-            constexpr bool PRO = decltype(pro_tag)::value != 0;
+            constexpr int MODE16 = decltype(pro_tag)::value;                // 0 steady state, 1 prologue, 2 tail
+            constexpr bool PRO = MODE16 == 1, TAILM = MODE16 == 2;
+            using UN = std::integral_constant<int, 1 - U>;
+            if (TAILM) {
+                // cells of this anti-diagonal inside the matrix (do_step's jlo / jhi) as one bit per cell
+                const int klo = max(-W, max(-dd, dd - 2 * (pr.qlen - 1)));
+                const int khi = min(W, min(dd, 2 * (pr.tcols - 1) - dd));
+                const int k0 = -W + 2 * C * gl + U;
+                const int a = max((klo - k0 + 1) >> 1, 0), b = min((khi - k0) >> 1, C - 1);
+                const unsigned fm = (b >= a) ? ((0xffffffffu >> (31 - b)) & (0xffffffffu << a)) : 0u;
+                vm2 = (fm & ((1u << P) - 1u)) | ((fm >> P) << 16);
+            }
             if (U == 0) {
                 unsigned x = __shfl_up_sync(FULL, AE[P - 1], 1);             // neighbour's (E[P-1], E[C-1])
                 if (lane == 0) {
@@ -735,19 +799,21 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                     else x = (unsigned)(((dd == W) ? (-(p.goe + p.ge * W) - p.goe - base) : FLOOR16) + BIAS16) << 16;
                 }
                 const unsigned ein = prmt(x, AE[P - 1], 0x5432);             // lo: neighbour's E[C-1], hi: own E[P-1]
-                const unsigned best2 = step_cells16<C, 0>(A0, AE, AF, Qw, Rw, ein, p, mge2, mgoe32, floor2);
+                const unsigned best2 = step_cells16<C, 0, TAILM>(A0, AE, AF, Qw, Rw, ein, p, mge2, mgoe32, floor2, vm2);
                 if (edge_lane) AE[JP] = JH ? ((AE[JP] & 0xffffu) | (FLOORU16 << 16)) : ((AE[JP] & 0xffff0000u) | FLOORU16);
                 shift_ref();
-                return scan_fast(best2, A0, dd, 0);
+                if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }   // inputs of the next anti-diagonal
+                return scan_fast(best2, A0, dd, 0, TAILM);
             } else {
                 unsigned y = __shfl_down_sync(FULL, AF[0], 1);               // neighbour's (F[0], F[P])
                 if (lane == 31) y = FLOORU16;                                // right of the last lane: dead
                 const unsigned fin = prmt(AF[0], y, 0x5432);                 // lo: own F[P], hi: neighbour's F[0]
-                const unsigned best2 = step_cells16<C, 1>(A1, AE, AF, Qw, Rw, fin, p, mge2, mgoe32, floor2);
+                const unsigned best2 = step_cells16<C, 1, TAILM>(A1, AE, AF, Qw, Rw, fin, p, mge2, mgoe32, floor2, vm2);
                 // k = +W reads MINUS_INF2 from outside the band; in the prologue that cell is dead until F(0,W) is injected
                 if (!PRO) { if (edge_lane) AF[JP] = JH ? ((AF[JP] & 0xffffu) | ((unsigned)(neg16 + BIAS16) << 16)) : ((AF[JP] & 0xffff0000u) | (unsigned)(neg16 + BIAS16)); }
                 shift_query();
-                return scan_fast(best2, A1, dd, 1);
+                if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }
+                return scan_fast(best2, A1, dd, 1, TAILM);
             }
         };
         // inject_static on the packed arrays: cell j = 4Q + pos lives in register (4Q + pos) % P, half Q / (NG/2); the value
@@ -782,111 +848,123 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 else        { A1[4 * R + PT] = prmt(A1[4 * R + PT], hv2, sh_); A1[4 * R + PL] = prmt(A1[4 * R + PL], hv2, sl_); }
             }
         };
-        // One aligned block of 8 prologue anti-diagonals as straight-line code with re-entry points: a step whose
-        // anti-diagonal might fire Z-drop leaves the block (returns 1 + 2*offset); the caller looks at it outside of the hot
-        // code (scan_slow: two searches, ~300 instructions) and comes back through `entry` to the injection that follows that
-        // step. Keeping the cold code out of the block matters: at 8 x ~200 instructions the block just fits the 32 KB
-        // instruction cache, with the scan inlined eight times it did not (ncu: 3 of 4 issue slots lost to instruction fetch).
-        // The scan -- including the search for the position of a low maximum -- runs BEFORE the injection, so an injected
-        // edge value can never be mistaken for the anti-diagonal's maximum.
+        // The prologue loop: two anti-diagonals per iteration; the place of the pair inside its block of 8 (S) only selects
+        // which of four small injection bodies runs (a warp-uniform switch). The executed path of an iteration is ~400
+        // instructions -- it has to be small: an earlier version with the 8 anti-diagonals of a block as straight-line code
+        // (1,700 instructions, 26 KB) lost 3 of 4 issue slots to instruction fetch (ncu: no_instruction 2.6 warps per issue,
+        // I-cache hit rate 62 %). The scan -- including the search for the position of a low maximum -- runs BEFORE the
+        // injection, so an injected edge value can never be mistaken for the anti-diagonal's maximum.
         using PRO1 = std::integral_constant<int, 1>;
         using PRO0 = std::integral_constant<int, 0>;
-        auto pro_block16 = [&](int d0, int entry) -> int {
-            switch (entry) {
-            case 0:  if (step16(d0, UA{}, PRO1{})) return 1;
-            [[fallthrough]];
-            case 1:  inject16(d0, UA{}, S0{});
-                     if (step16(d0 + 1, UB{}, PRO1{})) return 3;
-            [[fallthrough]];
-            case 3:  inject16(d0 + 1, UB{}, S0{});
-                     if (step16(d0 + 2, UA{}, PRO1{})) return 5;
-            [[fallthrough]];
-            case 5:  inject16(d0 + 2, UA{}, S1{});
-                     if (step16(d0 + 3, UB{}, PRO1{})) return 7;
-            [[fallthrough]];
-            case 7:  inject16(d0 + 3, UB{}, S1{});
-                     if (step16(d0 + 4, UA{}, PRO1{})) return 9;
-            [[fallthrough]];
-            case 9:  inject16(d0 + 4, UA{}, S2{});
-                     if (step16(d0 + 5, UB{}, PRO1{})) return 11;
-            [[fallthrough]];
-            case 11: inject16(d0 + 5, UB{}, S2{});
-                     if (step16(d0 + 6, UA{}, PRO1{})) return 13;
-            [[fallthrough]];
-            case 13: inject16(d0 + 6, UA{}, S3{});                          // d0 + 6 <= W - 1: always an injection
-                     if (step16(d0 + 7, UB{}, PRO1{})) return 15;
-            [[fallthrough]];
-            default: if (d0 + 7 < W) inject16(d0 + 7, UB{}, S3{});          // nothing after the anti-diagonal d == W
+        auto inject16_sw = [&](int dd, auto u_tag, int S) {
+            switch (S) {
+            case 0: inject16(dd, u_tag, S0{}); break;
+            case 1: inject16(dd, u_tag, S1{}); break;
+            case 2: inject16(dd, u_tag, S2{}); break;
+            default: inject16(dd, u_tag, S3{}); break;
             }
-            return 0;
         };
         if (d == 0) {
-            // the whole prologue in aligned blocks of 8 (the caller guarantees STATIC_PRO, p.s16 & 2 and W + 1 < d_tail). Inside
-            // it no value can leave the 16-bit range (host-side bound, engine.cu), so there is no range check and no bail-out.
-            int entry = 0;
+            // the whole prologue, d = 0 .. W (the caller guarantees STATIC_PRO, p.s16 & 2 and W + 1 < d_tail). Inside it no value
+            // can leave the 16-bit range (host-side bound, engine.cu), so there is no range check and no bail-out.
             for (;;) {
                 int ev = 0;
 #pragma unroll 1
-                for (; d + 7 <= W; d += 8) {
-                    blk_qt = ((d + W + 1) >> 3) - NG * gl;
-                    blk_ql = ((W + 1 - d) >> 3) - 1 - NG * gl;
-                    blk_last = (d + 7 == W);
-                    block_selectors();
-                    ev = pro_block16(d, entry);
-                    entry = 0;
-                    if (ev) break;
+                for (; d < W; d += 2) {
+                    const int S = (d >> 1) & 3;
+                    if (S == 0) {                                            // a new block of 8
+                        blk_qt = ((d + W + 1) >> 3) - NG * gl;
+                        blk_ql = ((W + 1 - d) >> 3) - 1 - NG * gl;
+                        blk_last = (d + 7 == W);
+                        block_selectors();
+                    }
+                    if (step16(d, UA{}, PRO1{})) { ev = 1; break; }
+                    inject16_sw(d, UA{}, S);                                 // d <= W - 1: always an injection
+                    if (step16(d + 1, UB{}, PRO1{})) { ev = 2; break; }
+                    if (d + 1 < W) inject16_sw(d + 1, UB{}, S);              // nothing after the anti-diagonal d == W
                 }
                 if (!ev) break;
-                const int o = ev >> 1;                                       // the anti-diagonal d + o needs a closer look
-                const bool u1 = ((o & 1) == 0) == WODD;                      // even offsets are UA steps: parity class 1 iff W is odd
-                if (u1 ? scan_slow(A1, d + o, 1) : scan_slow(A0, d + o, 0)) { resolve(); d += o; return 1; }
-                entry = ev;                                                  // back into the same block, at the injection after that step
+                // cold: a closer look at the anti-diagonal that might fire, then finish the pair
+                const int S = (d >> 1) & 3;
+                if (ev == 1) {
+                    if (WODD ? scan_slow(A1, d, 1) : scan_slow(A0, d, 0)) { resolve(); return 1; }
+                    inject16_sw(d, UA{}, S);
+                    if (step16(d + 1, UB{}, PRO1{})) ev = 2;
+                }
+                if (ev == 2) {
+                    if (WODD ? scan_slow(A0, d + 1, 0) : scan_slow(A1, d + 1, 1)) { resolve(); d++; return 1; }
+                }
+                if (d + 1 < W) inject16_sw(d + 1, UB{}, S);
+                d += 2;
             }
             if (!check_range()) { resolve(); unpack(); return 2; }
         } else
         if (!check_range()) return 2;                                        // 32-bit arrays untouched so far
-        for (;;) {
-            // hot loop: up to 32 anti-diagonals between two range checks, left early only for a possible Z-drop
-            const int dchunk = min(d_fast_hi, d + 32);
-            int ev = 0;
+        using TAIL2 = std::integral_constant<int, 2>;
+        // hot loops: up to 32 anti-diagonals between two range checks, left early only for a possible Z-drop. The same
+        // structure runs twice: the steady state up to d_fast_hi, then (p.s16 & 4) the tail up to d_end16.
+        auto run_chunks = [&](int d_hi, auto mode_tag) -> int {             // 0: reached d_hi, 1: Z-drop on d, 2: range, 3: band exit at d
+            constexpr bool TAILM = decltype(mode_tag)::value == 2;
+            int next_slice = 0;
+            if (TAILM) { const int span = 8 * p.sw; next_slice = ((d + span - 1) / span) * span; }
+            for (;;) {
+                if (TAILM) {
+                    // leave well before an anti-diagonal could have no cell inside matrix and band (the reference then reads an
+                    // empty ring slot, scan_update's special case): the valid range shrinks by at most 2 per anti-diagonal
+                    const int klo = max(-W, max(-d, d - 2 * (pr.qlen - 1))), khi = min(W, min(d, 2 * (pr.tcols - 1) - d));
+                    if (khi - klo < 80) return 0;
+                }
+                const int dchunk = min(d_hi, d + 32);
+                int ev = 0;
 #pragma unroll 1
-            for (; d < dchunk; d += 2) {
-                if (step16(d, UA{}, PRO0{})) { ev = 1; break; }
-                if (step16(d + 1, UB{}, PRO0{})) { ev = 2; break; }
+                for (; d < dchunk; d += 2) {
+                    if (TAILM) {
+                        if (d == next_slice) {
+                            // slice bounds, agatha_kernel.h:183-191 (same arithmetic as the 32-bit driver below)
+                            const int i = d >> 3;
+                            int ss = max(0, i - pr.pq + 1);
+                            ss = max(ss, (i * 8 + 8 - W) / 2 / 8);
+                            int se = min(pr.pt - 1, i + p.sw - 1);
+                            se = min(se, ((i + p.sw - 1) * 8 + 7 + W) / 2 / 8);
+                            if (ss > se) { ev = 3; break; }
+                            next_slice += 8 * p.sw;
+                        }
+                    }
+                    if (step16(d, UA{}, mode_tag)) { ev = 1; break; }
+                    if (step16(d + 1, UB{}, mode_tag)) { ev = 2; break; }
+                }
+                if (ev == 3) return 3;
+                if (ev == 1) {
+                    if (WODD ? scan_slow(A1, d, 1) : scan_slow(A0, d, 0)) return 1;
+                    if (step16(d + 1, UB{}, mode_tag)) ev = 2;                   // finish the pair (cold copy of the second step)
+                    else d += 2;
+                }
+                if (ev == 2) {
+                    if (WODD ? scan_slow(A0, d + 1, 0) : scan_slow(A1, d + 1, 1)) { d++; return 1; }
+                    d += 2;
+                }
+                if (d >= d_hi) return 0;
+                if (!check_range()) return 2;
             }
-            if (ev == 1) {
-                if (WODD ? scan_slow(A1, d, 1) : scan_slow(A0, d, 0)) { resolve(); return 1; }
-                if (step16(d + 1, UB{}, PRO0{})) ev = 2;                             // finish the pair (cold copy of the second step)
-                else d += 2;
-            }
-            if (ev == 2) {
-                if (WODD ? scan_slow(A0, d + 1, 0) : scan_slow(A1, d + 1, 1)) { resolve(); d++; return 1; }
-                d += 2;
-            }
-            if (d >= d_fast_hi) break;
-            if (!check_range()) { resolve(); unpack(); return 2; }
+        };
+        if (d < d_fast_hi) {
+            const int rc = run_chunks(d_fast_hi, PRO0{});
+            if (rc == 1) { resolve(); return 1; }
+            if (rc == 2) { resolve(); unpack(); return 2; }
+        }
+        // the tail: cells beyond the far matrix edges are masked out of the maximum, padding columns are patched, the slice
+        // schedule is checked for band exit. The last anti-diagonals (and the wrap-up scan) are left to the 32-bit driver.
+        const int d_end16 = (min(pr.L, 8 * pr.total) - 2) & ~1;
+        if ((p.s16 & 4) && d == d_fast_hi && d > W && d < d_end16) {
+            in_tail = true;
+            if (has_phantom) phantom_patch16(d, UA{});                        // first tail step after the steady state
+            const int rc = run_chunks(d_end16, TAIL2{});
+            if (rc == 1) { resolve(); return 1; }
+            if (rc == 2) { resolve(); unpack(); return 2; }
+            if (rc == 3) { resolve(); return 3; }
         }
         resolve();
         unpack();
-        return 0;
-    };
-
-    // aligned block of 8 prologue anti-diagonals, none of them near the far edges (slices are multiples of 8);
-    // returns 0, or 1 + the offset of the anti-diagonal on which Z-drop fired
-    auto pro_block = [&](int d) -> int {
-        if constexpr (STATIC_PRO) {
-            blk_qt = ((d + W + 1) >> 3) - NG * gl;
-            blk_ql = ((W + 1 - d) >> 3) - 1 - NG * gl;
-            blk_last = (d + 7 == W);
-            if (do_step(d,     true, UA{}, M4{}, S0{})) return 1;
-            if (do_step(d + 1, true, UB{}, M4{}, S0{})) return 2;
-            if (do_step(d + 2, true, UA{}, M4{}, S1{})) return 3;
-            if (do_step(d + 3, true, UB{}, M4{}, S1{})) return 4;
-            if (do_step(d + 4, true, UA{}, M4{}, S2{})) return 5;
-            if (do_step(d + 5, true, UB{}, M4{}, S2{})) return 6;
-            if (do_step(d + 6, true, UA{}, M4{}, S3{})) return 7;
-            if (do_step(d + 7, true, UB{}, M4{}, S3{})) return 8;
-        }
         return 0;
     };
 
@@ -919,12 +997,13 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             }
             dend = 8 * (i + p.sw);
         }
-        bool fired = false, reslice = false;
+        bool fired = false, reslice = false, band_exit = false;
         while (d < dend) {
             if ((d >= d_fast_lo && d < d_fast_hi) || (CAN16 && STATIC_PRO && d == 0 && allow16 && (p.s16 & 2) && d_fast_lo < d_fast_hi)) {
                 if (CAN16 && allow16) {
                     const int rc = run_fast16(d);          // may cross slice boundaries: re-derive the slice afterwards
                     if (rc == 1) { fired = true; break; }
+                    if (rc == 3) { stop = AGATHA_STOP_BANDEXIT; d_stop = min(d, pr.L); band_exit = true; break; }   // at a slice start of the tail
                     if (rc == 2) allow16 = false;
                     reslice = true;
                     break;
@@ -936,16 +1015,23 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                     if (do_step(d + 1, true, UB{}, M0{}, S0{})) { fired = true; d++; break; }
                 }
                 if (fired) break;
-            } else if (STATIC_PRO && (d & 7) == 0 && d + 7 <= W && d + 7 < d_tail) {
-                const int off = pro_block(d);
-                if (off) { d += off - 1; fired = true; break; }
-                d += 8;
             } else {
                 if (has_phantom && d == d_fast_hi && d > 0) phantom_patch(d, UA{});   // first SLOW step after the FAST run
                 const bool s0 = wrap || d < pr.L, s1 = wrap || d + 1 < pr.L;
                 const bool far = d + 1 >= d_tail, near = d < W;                      // which matrix edges touch this pair of steps
                 bool f0, f1 = false;
-                if (!far)       { f0 = do_step(d, s0, UA{}, M1{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M1{}, S0{}); }
+                if (!far) {
+                    if constexpr (STATIC_PRO) {
+                        const int d0 = d & ~7;                                   // the aligned block of 8 this pair belongs to
+                        blk_qt = ((d0 + W + 1) >> 3) - NG * gl;
+                        blk_ql = ((W + 1 - d0) >> 3) - 1 - NG * gl;
+                        blk_last = (d0 + 7 == W);
+                        blk_S = (d >> 1) & 3;
+                        f0 = do_step(d, s0, UA{}, M4{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M4{}, S0{});
+                    } else {
+                        f0 = do_step(d, s0, UA{}, M1{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M1{}, S0{});
+                    }
+                }
                 else if (!near) { f0 = do_step(d, s0, UA{}, M2{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M2{}, S0{}); }
                 else            { f0 = do_step(d, s0, UA{}, M3{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M3{}, S0{}); }
                 if (f0) { fired = true; break; }
@@ -954,6 +1040,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             }
         }
         if (fired) { if (d < pr.L) { stop = AGATHA_STOP_ZDROP; d_stop = d + 1; } break; }
+        if (band_exit) break;
         if (reslice) continue;
         if (wrap) break;
     }

@@ -123,7 +123,7 @@ def test_zdrop_and_band_shifts_inside_the_prologue(oracle, w, monkeypatch):
         pkw = dict(pkw, band_width=w)
         exp = oracle.align_pairs(pairs, op.make_params(**pkw))
         res = {}
-        for mode in ("2", "1", "0"):                                               # packed prologue / packed steady state only / 32-bit
+        for mode in ("2", "7", "1", "0"):                                          # default (packed prologue + steady state) / + packed tail / steady state only / 32-bit
             monkeypatch.setenv("AGATHA_S16", mode)
             res[mode] = ag.align_pairs_device(pairs, ag.make_params(**pkw))
         for mode, got in res.items():
@@ -134,3 +134,25 @@ def test_zdrop_and_band_shifts_inside_the_prologue(oracle, w, monkeypatch):
             ds = exp["d_stop"][exp["stop"] == 1]
             if pkw["z_threshold"] == 20:
                 assert len(set(int(x) % 8 for x in ds if x <= w)) == 8             # fired on every place of a block
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_packed_tail_opt_in_matches_oracle(oracle, seed, monkeypatch):
+    """AGATHA_S16=7 also runs the far-edge part of the alignment on packed state (valid-cell masks, padding-column patches
+    and the slice-wise band-exit check inside the packed loop). Off by default; must still be bit-exact."""
+    import agatha_b200 as ag
+    from pairgen import make_pair
+    monkeypatch.setenv("AGATHA_S16", "7")
+    rng = np.random.default_rng(7000 + seed)
+    W = int(rng.choice([127, 255, 511, 751, 1023]))
+    pkw = dict(band_width=W, slice_width=int(rng.choice([1, 3, 7])), z_threshold=int(rng.choice([-1, 100, 400, 5000])),
+               match=int(rng.choice([1, 2])), mismatch=int(rng.choice([2, 4])), gap_open=int(rng.choice([2, 6])), gap_extend=int(rng.choice([1, 2])))
+    pairs = make_pairs(7100 + seed, 120, 2 * W, 6 * W + 2000, mixed=True)
+    pairs += [make_pair(rng, int(rng.integers(3 * W, 5 * W + 1000)), err=0.06, skew=int(rng.integers(-2 * W, 3 * W))) for _ in range(40)]   # band exit
+    pairs += [make_pair(rng, int(rng.integers(3 * W, 5 * W + 1000)), err=0.06, tail=-1) for _ in range(20)]                               # junk tails
+    got = ag.align_pairs_device(pairs, ag.make_params(**pkw))
+    exp = oracle.align_pairs(pairs, op.make_params(**pkw))
+    for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
+        bad = np.nonzero(got[a] != exp[b])[0]
+        assert len(bad) == 0, f"{pkw}: {len(bad)} pairs differ in {a}, first {bad[0]}: gpu {got[bad[0]]} oracle {exp[bad[0]]} lens {len(pairs[bad[0]][0])},{len(pairs[bad[0]][1])}"
+    assert len(set(exp["stop"])) >= 2
