@@ -107,8 +107,9 @@ int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
         const bool only_steady = env && env[0] == '1' && env[1] == '\0', with_tail = env && env[0] == '7' && env[1] == '\0';
         if (depth < 24000 && !only_steady) kp->s16 |= 2;
         // bit 2: the tail (far matrix edges) packed as well (it keeps the range monitor, so it needs no bound of its own).
-        // Opt-in (AGATHA_S16=7): bit-exact and 12-14 % faster on equal-length pairs, but on mixed-length batches the extra
-        // loop costs more in instruction fetch than it saves in issue slots (C1: 21.2 -> 27.0 ms, ncu: no_instruction 1.6 -> 2.9).
+        // Opt-in (AGATHA_S16=7) and only present in builds with -DAGATHA_TAIL16=1: bit-exact and 12-14 % faster on equal-length
+        // pairs, but on mixed-length batches the extra loop costs more in instruction fetch than it saves in issue slots
+        // (C1: 21.2 -> 27.0 ms, ncu: no_instruction 1.6 -> 2.9 warps per issue).
         if (with_tail) kp->s16 |= 4;
     }
     return AGATHA_OK;

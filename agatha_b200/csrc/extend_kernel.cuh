@@ -24,6 +24,10 @@
 
 #include "agatha_b200.h"
 
+#ifndef AGATHA_TAIL16
+#define AGATHA_TAIL16 0
+#endif
+
 namespace agatha {
 
 constexpr int NEG16 = -16384;        // the reference's MINUS_INF2 (gasal_kernels.h:39); exact value matters for parity
@@ -593,6 +597,11 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     // exit. Returns 0: reached d_fast_hi; 1: Z-drop fired on anti-diagonal d; 2: values left the safe 16-bit range at d,
     // state is back in the 32-bit arrays and the caller continues with the 32-bit loop.
     constexpr bool CAN16 = !GENERIC && NW == 1 && JWS >= 0 && C % 8 == 0;
+    // The packed tail is compiled only with -DAGATHA_TAIL16=1 (and then still needs AGATHA_S16=7 at run time): bit-exact and
+    // 12-14 % faster on equal-length pairs, but its mere presence costs the steady-state loop 15 instructions per two
+    // anti-diagonals (uniform-register pressure: loop invariants get recomputed inside the loop) and on mixed-length batches
+    // the extra loop costs more in instruction fetch than it saves.
+    constexpr bool TAIL16 = CAN16 && (AGATHA_TAIL16 != 0);
     auto run_fast16 = [&](int& d) -> int {
         constexpr int P = C / 2;
         constexpr int JP = (JWS >= 0 ? JWS : 0) % P, JH = (JWS >= 0 ? JWS : 0) / P;   // register / half holding the cell k = +W
@@ -719,7 +728,6 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         int ev_lane_h = 0, ev_hrel = 0;
         // tail: valid-cell bits of the anti-diagonal being computed (layout as in step_cells16) and the matching 16-bit masks
         unsigned vm2 = 0u;
-        bool in_tail = false;
         auto half_mask = [&](int jj) -> unsigned { return (unsigned)imad((int)((vm2 >> jj) & 0x00010001u), p.m16, 0); };
         auto scan_fast = [&](unsigned best2, const unsigned (&A)[P], int dd, int u, bool TAILM) -> bool {   // TAILM is a constant at every call site (a generic lambda here crashes cicc 12.9)
             const int lane_h = max(lo16(best2), hi16(best2));
@@ -737,13 +745,13 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
             ev_lane_h = lane_h; ev_hrel = hrel;
             return true;
         };
-        auto scan_slow = [&](const unsigned (&A)[P], int dd, int u) -> bool {
+        auto scan_slow = [&](const unsigned (&A)[P], int dd, int u, bool tailm = false) -> bool {   // tailm: a constant at every call site
             resolve();                                                       // the test needs (mt, mq)
             const unsigned who = __ballot_sync(FULL, ev_lane_h == ev_hrel);
             const int src = 31 - __clz((int)who);
             unsigned B[P];
 #pragma unroll
-            for (int jj = 0; jj < P; jj++) B[jj] = in_tail ? (A[jj] & half_mask(jj)) : A[jj];
+            for (int jj = 0; jj < P; jj++) B[jj] = tailm ? (A[jj] & half_mask(jj)) : A[jj];
             const int jb = __shfl_sync(FULL, search(B, ev_hrel), src);
             return scan_update(st, ev_hrel + base, C * src + jb, dd, u, p);
         };
@@ -901,8 +909,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         } else
         if (!check_range()) return 2;                                        // 32-bit arrays untouched so far
         using TAIL2 = std::integral_constant<int, 2>;
-        // hot loops: up to 32 anti-diagonals between two range checks, left early only for a possible Z-drop. The same
-        // structure runs twice: the steady state up to d_fast_hi, then (p.s16 & 4) the tail up to d_end16.
+        // the tail's loop (opt-in, p.s16 & 4): same structure as the steady state below plus the slice schedule
         auto run_chunks = [&](int d_hi, auto mode_tag) -> int {             // 0: reached d_hi, 1: Z-drop on d, 2: range, 3: band exit at d
             constexpr bool TAILM = decltype(mode_tag)::value == 2;
             int next_slice = 0;
@@ -935,28 +942,45 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 }
                 if (ev == 3) return 3;
                 if (ev == 1) {
-                    if (WODD ? scan_slow(A1, d, 1) : scan_slow(A0, d, 0)) return 1;
+                    if (WODD ? scan_slow(A1, d, 1, TAILM) : scan_slow(A0, d, 0, TAILM)) return 1;
                     if (step16(d + 1, UB{}, mode_tag)) ev = 2;                   // finish the pair (cold copy of the second step)
                     else d += 2;
                 }
                 if (ev == 2) {
-                    if (WODD ? scan_slow(A0, d + 1, 0) : scan_slow(A1, d + 1, 1)) { d++; return 1; }
+                    if (WODD ? scan_slow(A0, d + 1, 0, TAILM) : scan_slow(A1, d + 1, 1, TAILM)) { d++; return 1; }
                     d += 2;
                 }
                 if (d >= d_hi) return 0;
                 if (!check_range()) return 2;
             }
         };
-        if (d < d_fast_hi) {
-            const int rc = run_chunks(d_fast_hi, PRO0{});
-            if (rc == 1) { resolve(); return 1; }
-            if (rc == 2) { resolve(); unpack(); return 2; }
+        // The steady state is written out instead of going through run_chunks: the shared lambda cost its hot loop 15 extra
+        // (uniform-datapath) instructions per two anti-diagonals.
+        while (d < d_fast_hi) {
+            // hot loop: up to 32 anti-diagonals between two range checks, left early only for a possible Z-drop
+            const int dchunk = min(d_fast_hi, d + 32);
+            int ev = 0;
+#pragma unroll 1
+            for (; d < dchunk; d += 2) {
+                if (step16(d, UA{}, PRO0{})) { ev = 1; break; }
+                if (step16(d + 1, UB{}, PRO0{})) { ev = 2; break; }
+            }
+            if (ev == 1) {
+                if (WODD ? scan_slow(A1, d, 1) : scan_slow(A0, d, 0)) { resolve(); return 1; }
+                if (step16(d + 1, UB{}, PRO0{})) ev = 2;                     // finish the pair (cold copy of the second step)
+                else d += 2;
+            }
+            if (ev == 2) {
+                if (WODD ? scan_slow(A0, d + 1, 0) : scan_slow(A1, d + 1, 1)) { resolve(); d++; return 1; }
+                d += 2;
+            }
+            if (d >= d_fast_hi) break;
+            if (!check_range()) { resolve(); unpack(); return 2; }
         }
         // the tail: cells beyond the far matrix edges are masked out of the maximum, padding columns are patched, the slice
         // schedule is checked for band exit. The last anti-diagonals (and the wrap-up scan) are left to the 32-bit driver.
         const int d_end16 = (min(pr.L, 8 * pr.total) - 2) & ~1;
-        if ((p.s16 & 4) && d == d_fast_hi && d > W && d < d_end16) {
-            in_tail = true;
+        if constexpr (TAIL16) if ((p.s16 & 4) && d == d_fast_hi && d > W && d < d_end16) {
             if (has_phantom) phantom_patch16(d, UA{});                        // first tail step after the steady state
             const int rc = run_chunks(d_end16, TAIL2{});
             if (rc == 1) { resolve(); return 1; }
