@@ -534,7 +534,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
     // lies beyond them is dead (NEGBIG), so the maximum needs no mask. MODE 2 TAIL: far edges only -- mask the maximum,
     // patch the padding columns. MODE 3: both (pairs shorter than the band).
     // MODE 4: PRO with inject_static (blk_* describe the aligned block of 8 the step belongs to).
-    auto do_step = [&](int d, bool scan, auto u_tag, auto mode_tag, auto s_tag) -> bool {
+    auto do_step = [&](int d, bool scan, auto u_tag, auto mode_tag) -> bool {
         constexpr int U = decltype(u_tag)::value;
         constexpr int MODE = decltype(mode_tag)::value;
         constexpr bool FAST = MODE == 0, MASK = MODE == 2 || MODE == 3, INJECT = MODE == 1 || MODE == 3;
@@ -1035,8 +1035,8 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 const int dlim = min(dend, d_fast_hi);
 #pragma unroll 1
                 for (; d < dlim; d += 2) {
-                    if (do_step(d, true, UA{}, M0{}, S0{})) { fired = true; break; }
-                    if (do_step(d + 1, true, UB{}, M0{}, S0{})) { fired = true; d++; break; }
+                    if (do_step(d, true, UA{}, M0{})) { fired = true; break; }
+                    if (do_step(d + 1, true, UB{}, M0{})) { fired = true; d++; break; }
                 }
                 if (fired) break;
             } else {
@@ -1051,13 +1051,13 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                         blk_ql = ((W + 1 - d0) >> 3) - 1 - NG * gl;
                         blk_last = (d0 + 7 == W);
                         blk_S = (d >> 1) & 3;
-                        f0 = do_step(d, s0, UA{}, M4{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M4{}, S0{});
+                        f0 = do_step(d, s0, UA{}, M4{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M4{});
                     } else {
-                        f0 = do_step(d, s0, UA{}, M1{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M1{}, S0{});
+                        f0 = do_step(d, s0, UA{}, M1{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M1{});
                     }
                 }
-                else if (!near) { f0 = do_step(d, s0, UA{}, M2{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M2{}, S0{}); }
-                else            { f0 = do_step(d, s0, UA{}, M3{}, S0{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M3{}, S0{}); }
+                else if (!near) { f0 = do_step(d, s0, UA{}, M2{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M2{}); }
+                else            { f0 = do_step(d, s0, UA{}, M3{}); if (!f0) f1 = do_step(d + 1, s1, UB{}, M3{}); }
                 if (f0) { fired = true; break; }
                 if (f1) { fired = true; d++; break; }
                 d += 2;
