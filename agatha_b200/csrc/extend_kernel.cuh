@@ -88,13 +88,14 @@ __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel)
 //   H   : H of the parity-U cells (value from anti-diagonal d-2 on entry, d on exit)
 //   E,F : on entry outputs of the previous step (other parity); on exit outputs of this step
 //   Qw/Rw: nibble j of the windows holds the query/target code of cell j
-// Returns the lane's best tracking key max_j(H_j*32 + j) (ties -> largest j == largest target index).
+// Returns the lane's best tracking key max_j(H_j*32 + j) (ties -> largest j == largest target index); TAIL: only over the
+// cells whose bit is set in vmask (the cells inside the matrix).
 // Recurrence: CORE_COMPUTE, agatha_kernel.h:20-30 (gap opens from M = diag + s, not from H).
 // ---------------------------------------------------------------------------------------------------------------
 template <int C, int U, bool TAIL, bool GENERIC>
 __device__ __forceinline__ int step_cells(int (&H)[C], int (&E)[C], int (&F)[C],
                                           const uint32_t (&Qw)[(C + 7) / 8], const uint32_t (&Rw)[(C + 7) / 8],
-                                          int edge_in, const KernelParams& p, int jlo, int jhi)
+                                          int edge_in, const KernelParams& p, unsigned vmask)
 {
     constexpr int NWORD = (C + 7) / 8;
     unsigned sc[2 * NWORD];
@@ -133,7 +134,7 @@ __device__ __forceinline__ int step_cells(int (&H)[C], int (&E)[C], int (&F)[C],
         F[j] = __viaddmax_s32(fin, mge, t);
         H[j] = h;
         int key = imad(h, p.k32, j);
-        if (TAIL) key = (j >= jlo && j <= jhi) ? key : INT_MIN;
+        if (TAIL) key = ((vmask >> j) & 1u) ? key : INT_MIN;                       // one bit test per cell instead of two compares
         if (jj & 1) best = __vimax3_s32(best, pend, key); else pend = key;
     }
     if (C & 1) best = max(best, pend);
@@ -539,13 +540,14 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
         constexpr int MODE = decltype(mode_tag)::value;
         constexpr bool FAST = MODE == 0, MASK = MODE == 2 || MODE == 3, INJECT = MODE == 1 || MODE == 3;
         using UN = std::integral_constant<int, 1 - U>;
-        int jlo = 0, jhi = C - 1;
+        unsigned vmask = 0xffffffffu;                // cells of this lane inside the matrix, bit j <-> cell j
         if (MASK) {
             const int klo = max(-W, max(-d, d - 2 * (pr.qlen - 1)));
             const int khi = min(W, min(d, 2 * (pr.tcols - 1) - d));
             const int k0 = -W + 2 * C * gl + U;
-            jlo = (klo - k0 + 1) >> 1;               // ceil((klo-k0)/2)
-            jhi = (khi - k0) >> 1;
+            const int jlo = max((klo - k0 + 1) >> 1, 0);               // ceil((klo-k0)/2)
+            const int jhi = min((khi - k0) >> 1, C - 1);
+            vmask = (jhi >= jlo) ? ((0xffffffffu >> (31 - jhi)) & (0xffffffffu << jlo)) : 0u;
         }
         int best;
         if (U == 0) {
@@ -556,7 +558,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 if (NW == 1 || warp == 0) ein = (FAST || d > W) ? NEG16 : ((d == W) ? (-(p.goe + p.ge * W) - p.goe) : NEGBIG);
                 else ein = sm->edgeE[warp - 1];
             }
-            best = step_cells<C, 0, MASK, GENERIC>(H0, E, F, Qw, Rw, ein, p, jlo, jhi);
+            best = step_cells<C, 0, MASK, GENERIC>(H0, E, F, Qw, Rw, ein, p, vmask);
             if (JWS >= 0) { if (edge_lane) E[JWS >= 0 ? JWS : 0] = NEGBIG; } else poke<C>(E, jw_dyn, NEGBIG);   // nothing may leak into k = W+1
             shift_ref();
         } else {
@@ -565,7 +567,7 @@ __device__ __forceinline__ void run_pair(const Pair& pr, const KernelParams& p, 
                 if (NW == 1 || warp == NW - 1) fin = NEGBIG;
                 else fin = sm->edgeF[warp + 1];
             }
-            best = step_cells<C, 1, MASK, GENERIC>(H1, E, F, Qw, Rw, fin, p, jlo, jhi);
+            best = step_cells<C, 1, MASK, GENERIC>(H1, E, F, Qw, Rw, fin, p, vmask);
             // k = W reads MINUS_INF2 from outside the band (agatha_kernel.h:138); F(0,W) is injected below at d = W-1
             { const int v = (FAST || d + 1 > W) ? NEG16 : NEGBIG; if (JWS >= 0) { if (edge_lane) F[JWS >= 0 ? JWS : 0] = v; } else poke<C>(F, jw_dyn, v); }
             shift_query();
