@@ -4,10 +4,7 @@
 #include "agatha_b200.h"
 
 namespace agatha {
-struct KernelParams;
 int set_error(int code, const char* fmt, ...);
 int cuda_error(cudaError_t e, const char* what);
 void count_launch();
-int make_kernel_params(const agatha_params_t* p, KernelParams* kp);
-bool fast_table_ok(const agatha_params_t* p);
 }  // namespace agatha

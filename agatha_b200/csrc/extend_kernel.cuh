@@ -69,18 +69,27 @@ struct JobArrays {
 
 // Integer multiply-add that ptxas cannot strength-reduce to IADD3/LEA (b comes from the constant bank at run time).
 // ncu (profiles/extend_kernel_r01_ncu_full.csv): ALU pipe 81 % busy, FMA pipe 14 % -- every op moved here is free.
+// (AGATHA_HOST_EMU: tests/emu compiles this header for the CPU, where inline PTX has to be spelled in C.)
 __device__ __forceinline__ int imad(int a, int b, int c)
 {
+#ifdef AGATHA_HOST_EMU
+    return (int)((unsigned)a * (unsigned)b + (unsigned)c);
+#else
     int d;
     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+#endif
 }
 
 __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel)
 {
+#ifdef AGATHA_HOST_EMU
+    return __byte_perm(a, b, sel);
+#else
     unsigned d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------

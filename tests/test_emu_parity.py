@@ -1,0 +1,56 @@
+"""CPU tests of the CUDA kernel LOGIC: the product's kernel headers (agatha_b200/csrc/extend_kernel.cuh, pack_kernel.cuh)
+compiled for the host by the SIMT emulation under tests/emu (one fiber per CUDA thread, collectives as rendezvous) and
+compared bit-exactly with the oracle. This is test infrastructure: it proves nothing about the GPU build except that the
+same source, run with CUDA semantics, gives the oracle's results -- the `-m gpu` tests are the parity tests proper."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as op
+from pairgen import make_pairs
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from emu import emu as e
+    e.build()
+    return e
+
+
+def _cmp(emu, oracle, pairs, pkw, what="", s16=-1):
+    got = emu.align_pairs(pairs, emu.make_params(**pkw), s16_mode=s16)
+    exp = oracle.align_pairs(pairs, op.make_params(**pkw))
+    for a, b in (("score", "score"), ("query_end", "query_end"), ("target_end", "target_end"), ("stop", "stop"), ("dstop", "d_stop")):
+        bad = np.nonzero(got[a] != exp[b])[0]
+        assert len(bad) == 0, (f"{what} {pkw} s16={s16}: {len(bad)}/{len(pairs)} pairs differ in {a}; first idx {bad[0]}: "
+                               f"emu {got[bad[0]]} oracle {exp[bad[0]]} qlen {len(pairs[bad[0]][0])} tlen {len(pairs[bad[0]][1])}")
+
+
+@pytest.mark.parametrize("W", [0, 1, 7, 8, 15, 33, 63, 67, 75, 99, 100, 123, 127, 255, 263, 511])
+def test_emulated_kernel_vs_oracle_every_single_warp_shape(emu, oracle, W):
+    # includes the band widths 3 (mod 8) that once took the static-injection prologue by mistake
+    hi = 300 if W < 100 else 1400
+    _cmp(emu, oracle, make_pairs(9000 + W, 50, 1, hi, mixed=True), dict(band_width=W, z_threshold=100), "rand")
+    _cmp(emu, oracle, make_pairs(9100 + W, 20, max(W, 1), max(3 * W, 10), mixed=True), dict(band_width=W, slice_width=1, z_threshold=30), "rand sw1")
+
+
+@pytest.mark.parametrize("s16", [-1, 0, 1])
+def test_emulated_default_band_all_packed_modes(emu, oracle, s16):
+    pairs = make_pairs(77, 10, 1600, 3500, mixed=True) + make_pairs(78, 30, 1, 1500, mixed=True)
+    _cmp(emu, oracle, pairs, dict(), "w751", s16)
+    _cmp(emu, oracle, pairs[:16], dict(match=2, mismatch=5, gap_open=4, gap_extend=1, z_threshold=50, band_width=759), "w759", s16)
+
+
+@pytest.mark.parametrize("W,hi", [(1031, 2600), (2047, 4500), (4095, 6000)])
+def test_emulated_wide_bands_multi_warp_groups(emu, oracle, W, hi):
+    pairs = make_pairs(9700 + W, 6, 1, hi, mixed=True) + make_pairs(9800 + W, 2, hi, hi + 300, err=0.01)
+    _cmp(emu, oracle, pairs, dict(band_width=W), "wide")
+
+
+def test_emulated_edge_cases_and_rare_symbols(emu, oracle):
+    pairs = [("", "ACGT"), ("ACGT", ""), ("A", "A"), ("T", "A"), ("NNNN", "NNNN"), ("ACGTACGTA", "ACG"), ("ACG", "ACGTACGTACGT"),
+             ("acgtacgt", "ACGTACGT"), ("ACGTNACGT", "ACGTNACGT"), ("A" * 40, "A" * 40), ("ACGT" * 10, "TGCA" * 10)]
+    for W in (7, 15, 751):
+        _cmp(emu, oracle, pairs, dict(band_width=W), "edge")
+    _cmp(emu, oracle, make_pairs(300, 40, 100, 800, err=0.1, n_rate=0.05), dict(band_width=63), "nrich")
+    _cmp(emu, oracle, make_pairs(302, 40, 100, 800, err=0.1, iupac=True), dict(band_width=63), "iupac")
+    _cmp(emu, oracle, make_pairs(303, 20, 100, 800, err=0.1), dict(band_width=63, match=200, mismatch=300), "generic scoring")

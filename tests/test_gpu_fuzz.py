@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 def test_fuzz_parameters(oracle, seed):
     import agatha_b200 as ag
     rng = np.random.default_rng(1000 + seed)
-    W = int(rng.choice([0, 3, 7, 12, 15, 23, 31, 47, 63, 95, 127, 200, 255, 383, 511, 751, 767, 1000, 1023, 1500]))
+    W = int(rng.choice([0, 3, 7, 12, 15, 23, 31, 47, 63, 67, 75, 95, 99, 123, 127, 200, 255, 383, 511, 751, 767, 1000, 1023, 1500]))
     pkw = dict(band_width=W, slice_width=int(rng.choice([1, 2, 3, 4, 7, 8, 15])), z_threshold=int(rng.choice([-1, 0, 1, 5, 30, 100, 400, 5000])),
                match=int(rng.choice([1, 2, 3, 5])), mismatch=int(rng.choice([1, 2, 4, 6, 9])), gap_open=int(rng.choice([0, 1, 4, 6, 12])),
                gap_extend=int(rng.choice([1, 2, 3])))

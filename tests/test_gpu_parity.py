@@ -68,6 +68,10 @@ def test_even_and_odd_unaligned_band_widths(oracle):
     for W in (0, 1, 8, 10, 33, 100, 750):
         pairs = make_pairs(9500 + W, 150, 1, 900, mixed=True)
         _cmp_oracle(oracle, pairs, dict(band_width=W, z_threshold=100), "unaligned W")
+    # W = 3 (mod 8) with C = 4 cells per lane: must NOT take the compile-time-position prologue (engine dispatch)
+    for W in (67, 75, 83, 91, 99, 107, 115, 123):
+        pairs = make_pairs(9600 + W, 120, W + 1, 4 * W, mixed=True)
+        _cmp_oracle(oracle, pairs, dict(band_width=W, z_threshold=100), "W = 3 mod 8")
 
 
 def test_edge_cases(oracle):
