@@ -3,7 +3,8 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(PKG, "lib", "libagatha_b200.so")
+# AGATHA_B200_LIB: load another build of the same library (kernel A/B measurements, tools/kperf.py)
+_LIB_PATH = os.environ.get("AGATHA_B200_LIB") or os.path.join(PKG, "lib", "libagatha_b200.so")
 _lib = None
 
 STOP_END, STOP_ZDROP, STOP_BANDEXIT = 0, 1, 2

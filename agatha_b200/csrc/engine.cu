@@ -35,6 +35,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 struct CudaLauncher {
     const JobArrays& ja; const KernelParams& kp; cudaStream_t st;
     template <int C, int NW, bool WODD, int JWS> int run() const { return launch_variant<C, NW, WODD, JWS>(ja, kp, st); }
+    template <int C, int NW, int JWS> int run16() const { return launch16_variant<C, NW, JWS>(ja, kp, st); }
 };
 
 }  // namespace agatha
@@ -122,7 +123,15 @@ int agatha_extend_device(const uint32_t* d_query_packed, const uint32_t* d_targe
     ja.score = d_score; ja.qend = d_query_end; ja.tend = d_target_end; ja.stop = d_stop; ja.dstop = d_dstop;
     ja.counter = (unsigned*)d_workspace;
     ja.n = (int)n_alns;
+    ja.redo = 0;
     const CudaLauncher l{ja, kp, st};
+    // The packed kernel first (where it applies); it marks the pairs it cannot finish exactly and the general kernel,
+    // second queue counter, aligns those. Otherwise the general kernel aligns everything.
+    if (dispatch16_variant(kp, l, &rc)) {
+        if (rc) return rc;
+        ja.counter = (unsigned*)d_workspace + 1;
+        ja.redo = 1;
+    }
     if (dispatch_variant(kp, l, &rc)) return rc;
     return set_error(AGATHA_EUNSUPPORTED, "no kernel for band_width %d", kp.W);
 }

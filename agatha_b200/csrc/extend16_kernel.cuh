@@ -1,0 +1,747 @@
+// The 16-bit packed extension kernel: the whole alignment -- prologue, steady state, tail, wrap-up -- on packed state, for
+// one-warp AND multi-warp (wide band) shapes. Same results as extend_kernel (extend_kernel.cuh), which stays the general
+// kernel: pairs this kernel cannot finish exactly (symbols outside {A,C,G,T,N}, pairs shorter than the band, values that
+// leave the safe 16-bit window) are marked in their result slot (REDO_MARK) and extend_kernel, launched right after on the same stream, aligns them.
+//
+// Replaces agatha_kernel (AGAThA/src/kernels/agatha_kernel.h:49-431); parity spec: SURVEY.md Appendix A, oracle/agatha_oracle.c.
+//
+// Layout: cells are addressed by anti-diagonal d = q + r and diagonal k = r - q; global lane gl of a
+// group of NW warps owns the cells k = -W + 2*(C*gl + j) + u, j in [0,C), u in {0,1}. Register jj of each state array holds
+// cell jj in its low half and cell jj + C/2 in its high half, as UNSIGNED biased 16-bit numbers relative to a per-alignment
+// base, so VIADDMNMX.U16x2 / VIMNMX3.U16x2 update two cells per instruction and t = M - goe is one IMAD on the FMA pipe.
+// What differs from the packed loops inside extend_kernel (run_fast16):
+//   * no 32-bit state at all: half the live registers, no conversion code, no spills;
+//   * the anti-diagonal that holds the running maximum is snapshotted to SHARED memory (3-4 STS.128 per lane) instead of
+//     P registers; its position is searched only when a Z-drop test or the end of the alignment needs it;
+//   * the steady state runs in blocks of 16 anti-diagonals: the sequence feeds of a block are loaded once at its top (one
+//     coalesced word per lane and sequence), the inner two-anti-diagonal body carries no load, no bounds test;
+//   * multi-warp groups (W > 1023): lane-edge hand-over and per-warp maxima through shared memory, one barrier per
+//     anti-diagonal; range monitor, re-basing and events are decided group-wide so that all warps stay in lock step;
+//   * the tail runs packed to the very end, including the anti-diagonals without any cell and the wrap-up scan
+//     (agatha_kernel.h:334-356).
+#pragma once
+
+#include "extend_kernel.cuh"
+
+#ifndef AGATHA_MB24
+#define AGATHA_MB24 3
+#endif
+#ifndef AGATHA_MBW4
+#define AGATHA_MBW4 3
+#endif
+#ifndef AGATHA_INLINE_EVENTS
+#define AGATHA_INLINE_EVENTS 0
+#endif
+
+namespace agatha {
+
+template <int C, int NW>
+struct Shape16 {
+    static constexpr int P = C / 2;
+    static constexpr int groups = NW == 1 ? 4 : 1;                 // alignments in flight per CTA
+    static constexpr int warps = NW * groups;
+    static constexpr int threads = 32 * warps;
+    // register budget: C = 8/16/24 fit 128 registers (4 CTAs of 4 warps per SM), C = 32 gets 168 (3 CTAs)
+    static constexpr int min_blocks = NW == 1 ? (C <= 24 ? AGATHA_MB24 : 3) : (NW == 2 ? 6 : (NW == 4 ? AGATHA_MBW4 : 1));
+};
+
+// Scoring and recurrence constants of one alignment, held in plain registers: ptxas otherwise re-materialises them from the
+// constant bank inside the hot loop (12 moves per two anti-diagonals for the PRMT table alone).
+struct Consts16 {
+    unsigned tab_lo, tab_hi;   // PRMT lookup table: byte x -> score for code XOR x
+    unsigned mge2;             // -ge in both halves (two's complement)
+    int mgoe32;                // subtracts goe from both halves at once
+    int one;                   // 1, opaque to ptxas: keeps t = M*1 - goe on the FMA pipe
+    int m16;                   // 0xffff, opaque too: (bit pair) * 0xffff widens a valid-cell bit to a 16-bit mask on the FMA pipe
+};
+
+// One anti-diagonal step for the C cells of parity U owned by this lane, on packed state (see step_cells16 in
+// extend_kernel.cuh for the representation). Recurrence: CORE_COMPUTE, agatha_kernel.h:20-30 (gap opens from M = diag + s).
+// TAILM: `vm2` holds one bit per cell of this anti-diagonal that lies inside the matrix (cells 0..P-1 in bits 0.., cells
+// P..C-1 in bits 16..); the others still take part in the recurrence (nothing inside the matrix ever reads them) but are
+// kept out of the maximum. Returns the packed maximum of H.
+template <int C, int U, bool TAILM>
+__device__ __forceinline__ unsigned cells16(unsigned (&H)[C / 2], unsigned (&E)[C / 2], unsigned (&F)[C / 2],
+                                            const uint32_t (&Qw)[C / 8], const uint32_t (&Rw)[C / 8],
+                                            unsigned edge_in, const Consts16& k, unsigned vm2)
+{
+    constexpr int P = C / 2, NWORD = C / 8;
+    const unsigned floor2 = FLOORU16 * 0x10001u;
+    unsigned sc[2 * NWORD];
+#pragma unroll
+    for (int w = 0; w < NWORD; w++) {
+        const unsigned x = Qw[w] ^ Rw[w];
+        sc[2 * w] = prmt(k.tab_lo, k.tab_hi, x);
+        sc[2 * w + 1] = prmt(k.tab_lo, k.tab_hi, x >> 16);
+    }
+    unsigned best = 0u, pend = 0u;
+#pragma unroll
+    for (int t_ = 0; t_ < P; t_++) {
+        const int jj = (U == 0) ? (P - 1 - t_) : t_;          // U == 0 reads E[j-1] (old) -> walk downwards; U == 1 reads F[j+1] -> upwards
+        unsigned ein, fin;
+        if (U == 0) { ein = (jj == 0) ? edge_in : E[jj - 1]; fin = F[jj]; }
+        else        { ein = E[jj]; fin = (jj == P - 1) ? edge_in : F[jj + 1]; }
+        // sign-extended score pair: byte (a&3) of sc[a>>2] for cell a = jj, byte (b&3) of sc[b>>2] for cell b = jj + P
+        const int a = jj, b = jj + P;
+        const unsigned sel = (unsigned)(a & 3) | ((unsigned)((a & 3) | 8) << 4) | ((unsigned)(4 + (b & 3)) << 8) | ((unsigned)((4 + (b & 3)) | 8) << 12);
+        const unsigned s2 = prmt(sc[a >> 2], sc[b >> 2], sel);
+        const unsigned m = __viaddmax_u16x2(H[jj], s2, floor2);           // max(H(d-2,k) + s, FLOOR)
+        // (t before h: h can then take over m's register instead of being moved into place afterwards)
+        const unsigned t = (unsigned)imad((int)m, k.one, k.mgoe32);        // M - goe in both halves: no borrow, m >= FLOORU16 > goe
+        const unsigned h = __vimax3_u16x2(m, ein, fin);
+        E[jj] = __viaddmax_u16x2(ein, k.mge2, t);
+        F[jj] = __viaddmax_u16x2(fin, k.mge2, t);
+        H[jj] = h;
+        unsigned hm = h;
+        if (TAILM) hm = h & (unsigned)imad((int)((vm2 >> jj) & 0x00010001u), k.m16, 0);
+        if (t_ == 0) pend = hm;
+        else if (t_ == 1) best = __vimax3_u16x2(pend, hm, hm);
+        else if (t_ & 1) best = __vimax3_u16x2(best, pend, hm);
+        else pend = hm;
+    }
+    if (P & 1) best = __vimax3_u16x2(best, pend, pend);
+    return best;
+}
+
+template <int C, int NW>
+struct Shared16 {
+    unsigned snap[Shape16<C, NW>::warps][C / 2][32];   // snapshot of the anti-diagonal holding the running maximum: [warp][register][lane]
+    unsigned edgeE[NW];       // (E[P-1], E[C-1]) of lane 31 of each warp, published after steps of parity 1
+    unsigned edgeF[NW];       // (F[0], F[P]) of lane 0 of each warp, published after steps of parity 0
+    int scan_h[2][NW];        // per-warp maximum of the anti-diagonal (stored domain), slots alternate by anti-diagonal parity
+    int rng[2][NW];           // per-warp live minimum / maximum for the range monitor
+    int bcast;                // cell index found by the owner warp
+    unsigned job;
+};
+
+// One alignment on packed state. Returns false when the pair has to be redone by the general kernel (nothing written).
+template <int C, int NW, int JWS>
+__device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p, int lane, int warp, int cta_warp, Shared16<C, NW>* sm,
+                                           int& out_score, int& out_qend, int& out_tend, int& out_stop, int& out_dstop)
+{
+    static_assert(C % 8 == 0 && C <= 32 && JWS >= 0 && JWS < C && (JWS & 7) == 7, "packed kernel: C multiple of 8, W = 7 (mod 8)");
+    constexpr int P = C / 2, NWORD = C / 8, NG = C / 4, NGH = NG / 2;
+    constexpr int JP = JWS % P, JH = JWS / P;          // register / half holding the cell k = +W
+    using U1 = std::integral_constant<int, 1>;          // parity class of even anti-diagonals (W is odd)
+    using U0 = std::integral_constant<int, 0>;
+    using S0 = std::integral_constant<int, 0>;
+    using S1 = std::integral_constant<int, 1>;
+    using S2 = std::integral_constant<int, 2>;
+    using S3 = std::integral_constant<int, 3>;
+    using MSTEADY = std::integral_constant<int, 0>;
+    using MPRO = std::integral_constant<int, 1>;
+    using MTAIL = std::integral_constant<int, 2>;
+    const int W = p.W;
+    const int gl = 32 * warp + lane;
+    const bool edge_lane = (gl == p.LW), dead_lane = gl > p.LW;
+
+    // ---- what this kernel does not handle --------------------------------------------------------------------------
+    // first d whose valid k-range is clipped by the far matrix edges (tlen, not tcols: padding columns need the tail's patches)
+    const int d_tail = min(2 * pr.qlen - 2 - W, 2 * pr.tlen - 2 - W) + 1;
+    const int d_fast_hi = min(d_tail - 1, pr.L - 1) & ~1;
+    if (W + 1 >= d_fast_hi) return false;                               // pair not longer than the band: general kernel
+    if (has_rare_symbols(pr, lane)) return false;                      // PRMT table scores {A,C,G,T,N} only
+
+    // ---- state -----------------------------------------------------------------------------------------------------------
+    const unsigned floor2 = pack16(FLOOR16, FLOOR16);
+    Consts16 k;
+    k.tab_lo = p.tab_lo; k.tab_hi = p.tab_hi;
+    k.mge2 = pack16raw(-p.ge, -p.ge);
+    k.mgoe32 = -(int)((unsigned)p.goe | ((unsigned)p.goe << 16));
+    k.one = p.one; k.m16 = p.m16;
+    {
+        // ptxas keeps warp-uniform values in uniform registers and copies them into a vector register in front of every PRMT
+        // (the table operand cannot be uniform): 12 moves per two anti-diagonals. A value that went through a shuffle is not
+        // uniform in its eyes, so the table stays in two ordinary registers for the whole alignment.
+        const unsigned z = __shfl_sync(FULL, 0u, lane);
+        k.tab_lo ^= z; k.tab_hi ^= z;
+    }
+    unsigned A0[P], A1[P], AE[P], AF[P];
+#pragma unroll
+    for (int jj = 0; jj < P; jj++) { A0[jj] = floor2; A1[jj] = floor2; AE[jj] = floor2; AF[jj] = floor2; }
+    int base = 0;                                                        // packed value = true value - base (+ BIAS16 as stored)
+
+    // sequence windows at d = 0: nibble j <-> query[qtop - j], target[rbot + j]
+    int qtop = (W >> 1) - C * gl;
+    int rbot = ((1 - W) >> 1) + C * gl;
+    uint32_t Qw[NWORD], Rw[NWORD];
+#pragma unroll
+    for (int w = 0; w < NWORD; w++) { Qw[w] = 0u; Rw[w] = 0u; }
+#pragma unroll 1
+    for (int j = 0; j < C; j++) {
+        const unsigned qb = qbase(pr, qtop - j) << (4 * (j & 7)), tb = tbase(pr, rbot + j) << (4 * (j & 7));
+#pragma unroll
+        for (int w = 0; w < NWORD; w++) if (w == (j >> 3)) { Qw[w] |= qb; Rw[w] |= tb; }
+    }
+    uint32_t qfeed, rfeed;
+    auto refeed = [&]() {                                // feeds for the generic (one base at a time) window shifts
+        const int nq = qtop + 1, nb = rbot + C;
+        qfeed = load_qword(pr, nq >> 3) << (4 * (nq & 7));
+        rfeed = load_tword(pr, nb >> 3) >> (4 * (nb & 7));
+    };
+    refeed();
+    auto shift_query = [&]() {                           // qtop -> qtop + 1
+        const int nq = qtop + 1;
+        if ((nq & 7) == 0) qfeed = load_qword(pr, nq >> 3);
+#pragma unroll
+        for (int w = NWORD - 1; w > 0; w--) Qw[w] = __funnelshift_l(Qw[w - 1], Qw[w], 4);
+        Qw[0] = __funnelshift_l(qfeed, Qw[0], 4);
+        qfeed <<= 4;
+        qtop = nq;
+    };
+    auto shift_ref = [&]() {                             // rbot -> rbot + 1
+        const int nb = rbot + C;
+        if ((nb & 7) == 0) rfeed = load_tword(pr, nb >> 3);
+#pragma unroll
+        for (int w = 0; w < NWORD - 1; w++) Rw[w] = __funnelshift_r(Rw[w], Rw[w + 1], 4);
+        Rw[NWORD - 1] = __funnelshift_r(Rw[NWORD - 1], rfeed, 4);
+        rfeed >>= 4;
+        rbot++;
+    };
+    // the same shifts inside a steady-state block: the feed word was prepared at the top of the block
+    auto shift_query_blk = [&]() {
+#pragma unroll
+        for (int w = NWORD - 1; w > 0; w--) Qw[w] = __funnelshift_l(Qw[w - 1], Qw[w], 4);
+        Qw[0] = __funnelshift_l(qfeed, Qw[0], 4);
+        qfeed <<= 4;
+    };
+    auto shift_ref_blk = [&]() {
+#pragma unroll
+        for (int w = 0; w < NWORD - 1; w++) Rw[w] = __funnelshift_r(Rw[w], Rw[w + 1], 4);
+        Rw[NWORD - 1] = __funnelshift_r(Rw[NWORD - 1], rfeed, 4);
+        rfeed >>= 4;
+    };
+    // window positions as a function of the anti-diagonal about to be computed (even d)
+    auto window_pos = [&](int dd) { qtop = ((dd + W) >> 1) - C * gl; rbot = ((dd - W + 1) >> 1) + C * gl; };
+
+    // run-time cell index -> compare + select of a PRMT selector per register; j < 0 (another lane's cell) changes nothing
+    auto poke16 = [&](unsigned (&A)[P], int j, unsigned v2) {
+#pragma unroll
+        for (int jj = 0; jj < P; jj++) {
+            const unsigned sel = (j == jj) ? 0x3254u : ((j == jj + P) ? 0x7610u : 0x3210u);
+            A[jj] = prmt(A[jj], v2, sel);
+        }
+    };
+    auto own = [&](int g) { const int j = g - C * gl; return (j >= 0 && j < C) ? j : -1; };
+
+    // ---- boundary: H(-1,-1) = 0 and the virtual cells of "anti-diagonal -1" (agatha_kernel.h:126-148) -------------------
+    {
+        const int hv = -p.goe, gv = hv - p.goe;                       // H(-1,0) = H(0,-1) = -goe; F(0,0) = E(0,0) = that - goe
+        poke16(A1, own(W >> 1), pack16(0, 0));                       // k = 0 belongs to parity 1 (W odd)
+        const int jt = own((W + 1) >> 1);                              // top: (q=-1, r=0) at k = 1
+        poke16(A0, jt, pack16(hv, hv)); poke16(AF, jt, pack16(gv, gv));
+        const int jl = own((W - 1) >> 1);                              // left: (q=0, r=-1) at k = -1
+        poke16(A0, jl, pack16(hv, hv)); poke16(AE, jl, pack16(gv, gv));
+    }
+
+    ScanState st = {0, 0, 0, scan_threshold(0, p)};                    // agatha_kernel.h:158-161
+    int stop = AGATHA_STOP_END, d_stop = pr.L;
+    const bool has_phantom = pr.tcols > pr.tlen;
+
+    // Everything the hot loops compare against lives in the STORED domain (true - base + BIAS16), as ints.
+    // The running maximum lives in the STORED domain while the loops run (maxS = st.max - base + BIAS16); st.max / st.thr are
+    // brought up to date only where the cold paths need them. thrS = maxS - Z (or -1 when Z-drop is off; gap_extend < 0 never
+    // gets here), so thrS <= maxS and "nothing can happen on this anti-diagonal" (thrS <= h <= maxS) is ONE unsigned
+    // comparison: h - thrS <= spanS, with spanS = Z a constant of the launch (or maxS + 1).
+    const bool zoff = p.Z < 0;
+    int maxS, thrS;
+    unsigned spanS;
+    auto set_max = [&](int hS) {                                       // hot: a new maximum hS (stored domain)
+        maxS = hS;
+        thrS = zoff ? -1 : hS - p.Z;
+        spanS = zoff ? (unsigned)(hS + 1) : (unsigned)p.Z;
+    };
+    auto sync_state = [&]() { st.max = maxS - BIAS16 + base; st.thr = scan_threshold(st.max, p); };   // cold: before scan_update / output
+    set_max(0 - base + BIAS16);
+    int negS = max(NEG16 - base, FLOOR16) + BIAS16;                    // MINUS_INF2 as stored
+    // Between two range checks (32 anti-diagonals) the smallest live H falls by at most 16*mismatch and the largest rises by
+    // at most 16*match; M = H + s and t = M - goe must stay above the clamp, H + match below the top. Dead (out-of-band)
+    // cells creep upwards by `match` on equal bases: they are pushed back to the floor at every range check.
+    const int low_ok = FLOOR16 + 17 * max(max(p.mismatch, p.match), 1) + p.goe + 64 + BIAS16;
+    const int high_ok = TOP16 - 17 * max(p.match, 0) - 64 + BIAS16;
+
+    // ---- snapshot of the anti-diagonal that holds the running maximum (shared memory) ------------------------------------
+    int snap_d = -1, snap_u = 0, snap_src = 0, snap_w = 0, snap_h = 0;
+    // (scalar stores: a vector store would need the state registers in aligned quadruples, which costs moves in the hot path)
+    auto snapshot = [&](const unsigned (&A)[P], unsigned keep_bits, bool masked) {
+#pragma unroll
+        for (int jj = 0; jj < P; jj++) {
+            unsigned x = A[jj];
+            if (masked) x &= (unsigned)imad((int)((keep_bits >> jj) & 0x00010001u), p.m16, 0);   // cells outside the matrix never match
+            sm->snap[cta_warp][jj][lane] = x;
+        }
+    };
+    auto search = [&](const unsigned (&A)[P], int h) -> int {          // largest cell index whose stored value is h, -1 if none
+        int jl = -1, jh = -1;
+#pragma unroll
+        for (int jj = 0; jj < P; jj++) { if ((int)(A[jj] & 0xffffu) == h) jl = jj; if ((int)(A[jj] >> 16) == h) jh = jj + P; }
+        return jh >= 0 ? jh : jl;
+    };
+    // group-wide broadcast of a value computed by warp `w` (NW > 1 only; cold paths)
+    auto group_bcast = [&](int v, int w) -> int {
+        if (NW == 1) return v;
+        if (warp == w && lane == 0) sm->bcast = v;
+        __syncthreads();
+        const int r = sm->bcast;
+        __syncthreads();
+        return r;
+    };
+    auto resolve = [&]() {                                              // (mt, mq) of the running maximum
+        if (snap_d < 0) return;
+        int g = 0;
+        if (NW == 1 || warp == snap_w) {
+            unsigned S[P];
+#pragma unroll
+            for (int jj = 0; jj < P; jj++) S[jj] = sm->snap[cta_warp][jj][lane];
+            const int jb = __shfl_sync(FULL, search(S, snap_h), snap_src);
+            g = C * (32 * warp + snap_src) + jb;
+        }
+        g = group_bcast(g, snap_w);
+        const int k = -W + 2 * g + snap_u;
+        const int r = (snap_d + k) >> 1;
+        st.mt = r; st.mq = snap_d - r;
+        snap_d = -1;
+    };
+
+    // which halves of register jj are live in the band-edge lane: cell j is in band iff j <= JW (parity 0) / j < JW (parity 1)
+    auto keep_mask = [&](int jj, bool strict) -> unsigned {
+        const bool lo = strict ? (jj < JWS) : (jj <= JWS), hi = strict ? (jj + P < JWS) : (jj + P <= JWS);
+        return (lo ? 0xffffu : 0u) | (hi ? 0xffff0000u : 0u);
+    };
+
+    // ---- range monitor over the live H values (both parities) + re-basing; false = values leave the safe window --------
+    auto check_range = [&]() -> bool {
+        // push the dead positions back to the floor (lanes beyond the band; in the band-edge lane the cells beyond k = +W)
+#pragma unroll
+        for (int jj = 0; jj < P; jj++) {
+            const unsigned k0 = keep_mask(jj, false), k1 = keep_mask(jj, true);
+            if (dead_lane) { A0[jj] = floor2; A1[jj] = floor2; AE[jj] = floor2; AF[jj] = floor2; }
+            else if (edge_lane) {
+                A0[jj] = (A0[jj] & k0) | (floor2 & ~k0); A1[jj] = (A1[jj] & k1) | (floor2 & ~k1);
+                AE[jj] = (AE[jj] & k0) | (floor2 & ~k0); AF[jj] = (AF[jj] & k0) | (floor2 & ~k0);
+            }
+        }
+        unsigned mn2 = 0xffffffffu, mx2 = 0u;
+#pragma unroll
+        for (int jj = 0; jj < P; jj++) {
+            const unsigned x0 = A0[jj], x1 = A1[jj];
+            mx2 = __vimax3_u16x2(mx2, x0, x1);
+            const unsigned k0 = keep_mask(jj, false), k1 = keep_mask(jj, true);   // dead cells are out of the minimum
+            mn2 = __vimin3_u16x2(mn2, edge_lane ? (x0 | ~k0) : x0, edge_lane ? (x1 | ~k1) : x1);
+        }
+        int mn = (int)min(mn2 & 0xffffu, mn2 >> 16), mx = (int)max(mx2 & 0xffffu, mx2 >> 16);
+        if (dead_lane) mn = 65535;
+        mn = __reduce_min_sync(FULL, mn);
+        mx = __reduce_max_sync(FULL, mx);
+        if (NW > 1) {
+            if (lane == 0) { sm->rng[0][warp] = mn; sm->rng[1][warp] = mx; }
+            __syncthreads();
+            mn = __reduce_min_sync(FULL, lane < NW ? sm->rng[0][lane] : 65535);
+            mx = __reduce_max_sync(FULL, lane < NW ? sm->rng[1][lane] : 0);
+            __syncthreads();
+        }
+        if (mn < low_ok || mx > high_ok) return false;
+        if (mx > 8192 + BIAS16) {                                        // re-centre: rare (every ~8192 score units)
+            const int delta = min(mx - BIAS16, mn - low_ok);
+            if (delta > 0) {
+                // the packed add does not saturate: lift everything to FLOOR16 + delta first, then subtract
+                const unsigned md2 = pack16raw(-delta, -delta), lift2 = pack16(FLOOR16 + delta, FLOOR16 + delta);
+                auto shift_down = [&](unsigned x) { return __viaddmax_u16x2(__vimax3_u16x2(x, lift2, lift2), md2, floor2); };
+#pragma unroll
+                for (int jj = 0; jj < P; jj++) {
+                    A0[jj] = shift_down(A0[jj]); A1[jj] = shift_down(A1[jj]); AE[jj] = shift_down(AE[jj]); AF[jj] = shift_down(AF[jj]);
+                }
+                if (snap_d >= 0) {                                       // the snapshot is compared with stored values: move it along
+                    if (NW == 1 || warp == snap_w) {
+#pragma unroll
+                        for (int jj = 0; jj < P; jj++) sm->snap[cta_warp][jj][lane] = shift_down(sm->snap[cta_warp][jj][lane]);
+                    }
+                    snap_h -= delta;
+                }
+                base += delta;
+                negS = max(NEG16 - base, FLOOR16) + BIAS16;
+                set_max(maxS - delta);
+            }
+        }
+        if (NW > 1) {
+            // the hand-over slots hold values of the old base (and possibly dead cells that were just reset): publish again
+            if (lane == 31) sm->edgeE[warp] = AE[P - 1];
+            if (lane == 0) sm->edgeF[warp] = AF[0];
+            __syncthreads();
+        }
+        return true;
+    };
+
+    // ---- Termination Condition & Score Update (agatha_kernel.h:292-314) on a packed anti-diagonal -------------------------
+    // scan_fast runs in the hot loops: nothing to do, or a new maximum (snapshot for the lazy argmax); returns true when the
+    // anti-diagonal might fire Z-drop -> scan_slow, outside the hot loops.
+    int ev_lane_h = 0, ev_h = 0;
+    bool ev_empty = false;
+    unsigned vm2 = 0u;                                                   // tail: valid-cell bits of the anti-diagonal being computed
+    auto half_mask = [&](int jj) -> unsigned { return (unsigned)imad((int)((vm2 >> jj) & 0x00010001u), p.m16, 0); };
+    // maximum over the group of this lane's value; NW > 1: contains the group's barrier of this anti-diagonal
+    auto group_max = [&](int lane_h, int par) -> int {
+        int h = __reduce_max_sync(FULL, lane_h);
+        if (NW > 1) {
+            if (lane == 0) sm->scan_h[par][warp] = h;
+            __syncthreads();
+            h = __reduce_max_sync(FULL, lane < NW ? sm->scan_h[par][lane] : INT_MIN);
+        }
+        return h;
+    };
+    auto owner_warp = [&](int h, int par) -> int {                      // highest warp whose maximum is h (ties -> largest target index)
+        if (NW == 1) return 0;
+        const unsigned who = __ballot_sync(FULL, lane < NW && sm->scan_h[par][lane < NW ? lane : 0] == h);
+        return 31 - __clz((int)who);
+    };
+    auto scan_fast = [&](unsigned best2, const unsigned (&A)[P], int dd, int u, bool tailm) -> bool {   // tailm: constant at every call site
+        const int lane_h = (int)max(best2 & 0xffffu, best2 >> 16);
+        const int h = group_max(lane_h, dd & 1);
+        if ((unsigned)(h - thrS) <= spanS) return false;
+        if (h > maxS) {
+            const int ow = owner_warp(h, dd & 1);
+            if (NW == 1 || warp == ow) {
+                const unsigned who = __ballot_sync(FULL, lane_h == h);
+                snap_src = 31 - __clz((int)who);
+                snapshot(A, vm2, tailm);
+            }
+            snap_d = dd; snap_u = u; snap_w = ow; snap_h = h;
+            set_max(h);
+            return false;
+        }
+        ev_lane_h = lane_h; ev_h = h;
+        return true;
+    };
+    auto scan_slow = [&](const unsigned (&A)[P], int dd, int u, bool tailm) -> bool {   // tailm: constant at every call site
+        resolve();                                                       // the test needs (mt, mq) ...
+        sync_state();                                                    // ... and the maximum as a true score
+        if (ev_empty) { ev_empty = false; return scan_update(st, INT_MIN, 0, dd, u, p); }   // no cell on this anti-diagonal
+        const int ow = owner_warp(ev_h, dd & 1);
+        int g = 0;
+        if (NW == 1 || warp == ow) {
+            const unsigned who = __ballot_sync(FULL, ev_lane_h == ev_h);
+            const int src = 31 - __clz((int)who);
+            unsigned B[P];
+#pragma unroll
+            for (int jj = 0; jj < P; jj++) B[jj] = tailm ? (A[jj] & half_mask(jj)) : A[jj];
+            const int jb = __shfl_sync(FULL, search(B, ev_h), src);
+            g = C * (32 * warp + src) + jb;
+        }
+        g = group_bcast(g, ow);
+        return scan_update(st, ev_h - BIAS16 + base, g, dd, u, p);
+    };
+
+    // phantom (padding) target columns: their F and diagonal inputs restart from MINUS_INF2 at the first row of every slice
+    // chunk of the last target block (agatha_kernel.h:206-221 reload, :272-279 never stored); see oracle.
+    auto phantom_patch16 = [&](int dn, auto u_tag) {
+        constexpr int U = decltype(u_tag)::value;
+        const int qc = (dn - pr.tlen) & ~7;                              // the only multiple of 8 in (dn - tcols, dn - tlen]
+        if (dn - pr.tlen < 0 || dn - qc >= pr.tcols || qc >= pr.qlen) return;
+        if (!(qc == 0 || ((qc >> 3) + pr.pt - 1) % p.sw == 0)) return;
+        const int r = dn - qc, k = r - qc;
+        if (k > W || k < -W) return;
+        const unsigned v2 = (unsigned)negS * 0x10001u;
+        const int g = (k + W - U) >> 1;
+        const int gf = (U == 0) ? g : g + 1;                             // its F input: U==0 reads F[j], U==1 reads F[j+1]
+        poke16(AF, own(gf), v2);
+        if (r - 1 >= pr.tlen) { if (U == 0) poke16(A0, own(g), v2); else poke16(A1, own(g), v2); }
+    };
+
+    // ---- one packed anti-diagonal; true = scan_slow must look at it ---------------------------------------------------------
+    // MODE 0 steady state (every in-band cell inside the matrix); 1 prologue (d <= W: what lies beyond the matrix edges is
+    // dead, the caller injects the edge cells after the scan); 2 tail (far edges: cells outside the matrix are masked out of
+    // the maximum, padding columns are patched). BLK: inside a steady-state block (feeds prepared by the caller).
+    auto step16 = [&](int dd, bool scan, auto u_tag, auto mode_tag, auto blk_tag) -> bool {
+        constexpr int U = decltype(u_tag)::value;
+        constexpr int MODE = decltype(mode_tag)::value;
+        constexpr bool PRO = MODE == 1, TAILM = MODE == 2, BLK = decltype(blk_tag)::value != 0;
+        using UN = std::integral_constant<int, 1 - U>;
+        bool empty = false;
+        if (TAILM) {
+            // cells of this anti-diagonal inside the matrix (padding columns count: agatha_kernel.h CORE_COMPUTE has no r < tlen guard)
+            const int klo = max(-W, max(-dd, dd - 2 * (pr.qlen - 1)));
+            const int khi = min(W, min(dd, 2 * (pr.tcols - 1) - dd));
+            const int k0 = -W + 2 * C * gl + U;
+            const int a = max((klo - k0 + 1) >> 1, 0), b = min((khi - k0) >> 1, C - 1);
+            const unsigned fm = (b >= a) ? ((0xffffffffu >> (31 - b)) & (0xffffffffu << a)) : 0u;
+            vm2 = (fm & ((1u << P) - 1u)) | ((fm >> P) << 16);
+            // no cell at all: parity of the valid range included (k has the parity of dd)
+            empty = ((khi - ((khi ^ dd) & 1)) < (klo + ((klo ^ dd) & 1)));
+        }
+        unsigned best2;
+        if (U == 0) {
+            unsigned x = __shfl_up_sync(FULL, AE[P - 1], 1);             // neighbour's (E[P-1], E[C-1])
+            if (lane == 0) {
+                if (NW == 1 || warp == 0) {
+                    // left of k = -W: MINUS_INF2; in the prologue the cell is not real yet (dead), and on d == W its left
+                    // neighbour is the matrix-edge value E(W,0) (agatha_kernel.h:130)
+                    if (!PRO) x = (unsigned)negS << 16;
+                    else x = (unsigned)(((dd == W) ? (-(p.goe + p.ge * W) - p.goe - base) : FLOOR16) + BIAS16) << 16;
+                } else x = sm->edgeE[warp - 1];
+            }
+            const unsigned ein = prmt(x, AE[P - 1], 0x5432);             // lo: neighbour's E[C-1], hi: own E[P-1]
+            best2 = cells16<C, 0, TAILM>(A0, AE, AF, Qw, Rw, ein, k, vm2);
+            if (edge_lane) AE[JP] = JH ? ((AE[JP] & 0xffffu) | (FLOORU16 << 16)) : ((AE[JP] & 0xffff0000u) | FLOORU16);   // nothing leaks into k = W+1
+            if (BLK) shift_ref_blk(); else shift_ref();
+            if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }   // inputs of the next anti-diagonal
+            if (NW > 1) { if (lane == 0) sm->edgeF[warp] = AF[0]; }
+        } else {
+            unsigned y = __shfl_down_sync(FULL, AF[0], 1);               // neighbour's (F[0], F[P])
+            if (lane == 31) {
+                if (NW == 1 || warp == NW - 1) y = FLOORU16;             // right of the last lane: dead
+                else y = sm->edgeF[warp + 1];
+            }
+            const unsigned fin = prmt(AF[0], y, 0x5432);                 // lo: own F[P], hi: neighbour's F[0]
+            best2 = cells16<C, 1, TAILM>(A1, AE, AF, Qw, Rw, fin, k, vm2);
+            // k = +W reads MINUS_INF2 from outside the band; in the prologue that cell is dead until F(0,W) is injected
+            if (!PRO) { if (edge_lane) AF[JP] = JH ? ((AF[JP] & 0xffffu) | ((unsigned)negS << 16)) : ((AF[JP] & 0xffff0000u) | (unsigned)negS); }
+            if (BLK) shift_query_blk(); else shift_query();
+            if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }
+            if (NW > 1) { if (lane == 31) sm->edgeE[warp] = AE[P - 1]; }
+        }
+        if (!scan) {                                                     // computed, not scanned (d >= L before the wrap-up)
+            if (NW > 1) __syncthreads();
+            return false;
+        }
+        if (TAILM) {
+            if (empty) {                                                 // reads as an empty ring slot (agatha_kernel.h:152,296-299)
+                if (NW > 1) __syncthreads();
+                ev_empty = true;
+                return true;
+            }
+        }
+        return (U == 0) ? scan_fast(best2, A0, dd, 0, TAILM) : scan_fast(best2, A1, dd, 1, TAILM);
+    };
+
+    // ---- prologue: matrix-edge injection at compile-time positions inside aligned blocks of 8 anti-diagonals ----------------
+    // (see extend_kernel.cuh inject_static for the geometry.) The two virtual cells move by one cell every second
+    // anti-diagonal, in opposite directions; with W = 7 (mod 8) their position INSIDE a group of four cells is a compile-time
+    // function of the step's place S in its block; only the group is a run-time value, turned into PRMT selectors per block.
+    int blk_qt = 0, blk_ql = 0;
+    bool blk_last = false;
+    unsigned selT[NGH], selTn[NGH], selL[NGH], selLp[NGH];
+    auto block_selectors = [&]() {
+#pragma unroll
+        for (int R = 0; R < NGH; R++) {
+            auto pick = [&](int q) { return (q == R) ? 0x3254u : ((q == R + NGH) ? 0x7610u : 0x3210u); };
+            selT[R] = pick(blk_qt); selTn[R] = pick(blk_qt + 1);
+            selL[R] = pick(blk_ql); selLp[R] = pick(blk_ql - 1);
+        }
+    };
+    auto inject16 = [&](int dd, auto u_tag, auto s_tag) {
+        constexpr int U = decltype(u_tag)::value, S = decltype(s_tag)::value;
+        constexpr bool EVEN = (U == 1);
+        constexpr int PT = EVEN ? S : ((S + 1) & 3), PL = (2 - S) & 3;
+        const int hv = -(p.goe + p.ge * (dd + 1)) - base, gv = hv - p.goe;
+        const unsigned hv2 = pack16(hv, hv), gv2 = pack16(gv, gv);
+        const bool h_top = !(EVEN && S == 3 && blk_last);                 // d + 2 > W: only F is needed
+#pragma unroll
+        for (int R = 0; R < NGH; R++) {
+            const unsigned st_ = (!EVEN && S == 3) ? selTn[R] : selT[R];  // the odd step of S == 3 is already in the next group
+            const unsigned sl_ = (S == 3) ? selLp[R] : selL[R];           // ... and the left cell in the previous one
+            const unsigned sh_ = h_top ? st_ : 0x3210u;
+            AF[4 * R + PT] = prmt(AF[4 * R + PT], gv2, st_);
+            AE[4 * R + PL] = prmt(AE[4 * R + PL], gv2, sl_);
+            if (U == 0) { A0[4 * R + PT] = prmt(A0[4 * R + PT], hv2, sh_); A0[4 * R + PL] = prmt(A0[4 * R + PL], hv2, sl_); }
+            else        { A1[4 * R + PT] = prmt(A1[4 * R + PT], hv2, sh_); A1[4 * R + PL] = prmt(A1[4 * R + PL], hv2, sl_); }
+        }
+    };
+    auto inject16_sw = [&](int dd, auto u_tag, int S) {
+        switch (S) {
+        case 0: inject16(dd, u_tag, S0{}); break;
+        case 1: inject16(dd, u_tag, S1{}); break;
+        case 2: inject16(dd, u_tag, S2{}); break;
+        default: inject16(dd, u_tag, S3{}); break;
+        }
+    };
+
+    if (NW > 1) {
+        // hand-over slots must describe THIS alignment's initial state before the first step reads them
+        if (lane == 31) sm->edgeE[warp] = AE[P - 1];
+        if (lane == 0) sm->edgeF[warp] = AF[0];
+        __syncthreads();
+    }
+
+    int d = 0;
+    bool fired = false;
+    using NOBLK = std::integral_constant<int, 0>;
+    using INBLK = std::integral_constant<int, 1>;
+    // The prologue, d = 0 .. W. Inside it no value can leave the 16-bit range (host-side bound, extend_dispatch.h), so there
+    // is no range check. The scan -- including the search for the position of a low maximum -- runs BEFORE the injection, so
+    // an injected edge value can never be mistaken for the anti-diagonal's maximum.
+    for (;;) {
+        int ev = 0;
+#pragma unroll 1
+        for (; d < W; d += 2) {
+            const int S = (d >> 1) & 3;
+            if (S == 0) {                                                // a new block of 8
+                blk_qt = ((d + W + 1) >> 3) - NG * gl;
+                blk_ql = ((W + 1 - d) >> 3) - 1 - NG * gl;
+                blk_last = (d + 7 == W);
+                block_selectors();
+            }
+            if (step16(d, true, U1{}, MPRO{}, NOBLK{})) { ev = 1; break; }
+            inject16_sw(d, U1{}, S);                                     // d <= W - 1: always an injection
+            if (step16(d + 1, true, U0{}, MPRO{}, NOBLK{})) { ev = 2; break; }
+            if (d + 1 < W) inject16_sw(d + 1, U0{}, S);                  // nothing after the anti-diagonal d == W
+        }
+        if (!ev) break;
+        // cold: a closer look at the anti-diagonal that might fire, then finish the pair of steps
+        const int S = (d >> 1) & 3;
+        if (ev == 1) {
+            if (scan_slow(A1, d, 1, false)) { fired = true; break; }
+            inject16_sw(d, U1{}, S);
+            if (step16(d + 1, true, U0{}, MPRO{}, NOBLK{})) ev = 2;
+        }
+        if (ev == 2) {
+            if (scan_slow(A0, d + 1, 0, false)) { fired = true; d++; break; }
+        }
+        if (d + 1 < W) inject16_sw(d + 1, U0{}, S);
+        d += 2;
+    }
+
+    bool redo = false, band_exit = false;
+    int d_check = -64;                                                   // anti-diagonal of the last range check
+    if (!fired) {
+        // ---- steady state: blocks of 16 anti-diagonals, range check every second block --------------------------------------
+        while (d + 16 <= d_fast_hi && !fired && !redo) {
+            if (d - d_check >= 32) { if (!check_range()) { redo = true; break; } d_check = d; }
+            {
+                // feeds of the block: 8 query bases (first in the top nibble) and 8 target bases (first in the bottom nibble)
+                window_pos(d);
+                const int nq = qtop + 1, nb = rbot + C;
+                const uint32_t q0 = load_qword(pr, nq >> 3), q1 = load_qword(pr, (nq >> 3) + 1);
+                const uint32_t t0 = load_tword(pr, nb >> 3), t1 = load_tword(pr, (nb >> 3) + 1);
+                qfeed = __funnelshift_l(q1, q0, 4 * (nq & 7));
+                rfeed = __funnelshift_r(t0, t1, 4 * (nb & 7));
+            }
+            const int dblk = d + 16;
+#if AGATHA_INLINE_EVENTS
+#pragma unroll 1
+            for (; d < dblk; d += 2) {
+                if (step16(d, true, U1{}, MSTEADY{}, INBLK{})) { if (scan_slow(A1, d, 1, false)) { fired = true; break; } }
+                if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{})) { if (scan_slow(A0, d + 1, 0, false)) { fired = true; d++; break; } }
+            }
+#else
+            while (d < dblk) {
+                int ev = 0;
+#pragma unroll 1
+                for (; d < dblk; d += 2) {
+                    if (step16(d, true, U1{}, MSTEADY{}, INBLK{})) { ev = 1; break; }
+                    if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{})) { ev = 2; break; }
+                }
+                if (!ev) break;
+                if (ev == 1) {
+                    if (scan_slow(A1, d, 1, false)) { fired = true; break; }
+                    if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{})) ev = 2;   // finish the pair (cold copy of the second step)
+                }
+                if (ev == 2) {
+                    if (scan_slow(A0, d + 1, 0, false)) { fired = true; d++; break; }
+                }
+                d += 2;
+            }
+#endif
+        }
+        window_pos(d);                                                   // (d is even here unless fired)
+        refeed();
+    }
+
+    if (!fired && !redo) {
+        // ---- tail: the rest of the steady range, then the far matrix edges; slice schedule of the reference ----------------
+        // (agatha_kernel.h:180-330): band exit is tested at every slice start, diagonals d >= L are computed but not scanned,
+        // and when the slices end exactly on total_anti_diags 8 more anti-diagonals are scanned (wrap-up, :334-356).
+        const int span = 8 * p.sw;
+        const int n_slices = (pr.total + p.sw - 1) / p.sw;
+        const bool wrap = (pr.total % p.sw) == 0;
+        const int wrap_lo = wrap ? 8 * pr.total : INT_MAX;
+        const int d_end = wrap ? 8 * pr.total + 8 : min(pr.L, 8 * n_slices * p.sw);   // nothing observable beyond
+        int next_slice = ((d + span - 1) / span) * span;
+        if (has_phantom) phantom_patch16(d, U1{});                       // inputs of the first tail step
+        while (d < d_end && !fired && !redo && !band_exit) {
+            if (d - d_check >= 32) { if (!check_range()) { redo = true; break; } d_check = d; }
+            const int dchunk = min(d_end, d_check + 32);
+            int ev = 0;
+#pragma unroll 1
+            for (; d < dchunk; d += 2) {
+                if (d >= next_slice && d < 8 * pr.total) {
+                    // slice bounds, agatha_kernel.h:183-191 (truncating division as in the reference)
+                    const int i = next_slice >> 3;
+                    int ss = max(0, i - pr.pq + 1);
+                    ss = max(ss, (i * 8 + 8 - W) / 2 / 8);
+                    int se = min(pr.pt - 1, i + p.sw - 1);
+                    se = min(se, ((i + p.sw - 1) * 8 + 7 + W) / 2 / 8);
+                    if (ss > se) { ev = 3; break; }
+                    next_slice += span;
+                }
+                if (step16(d, d < pr.L || d >= wrap_lo, U1{}, MTAIL{}, NOBLK{})) { ev = 1; break; }
+                if (d + 1 < d_end) { if (step16(d + 1, d + 1 < pr.L || d + 1 >= wrap_lo, U0{}, MTAIL{}, NOBLK{})) { ev = 2; break; } }
+            }
+            if (ev == 3) { stop = AGATHA_STOP_BANDEXIT; d_stop = min(next_slice, pr.L); band_exit = true; break; }
+            if (ev == 1) {
+                if (scan_slow(A1, d, 1, true)) { fired = true; break; }
+                if (d + 1 < d_end) { if (step16(d + 1, d + 1 < pr.L || d + 1 >= wrap_lo, U0{}, MTAIL{}, NOBLK{})) ev = 2; }
+            }
+            if (ev == 2) {
+                if (scan_slow(A0, d + 1, 0, true)) { fired = true; d++; break; }
+            }
+            if (ev) d += 2;
+        }
+    }
+    if (redo) return false;
+    if (fired) { if (d < pr.L) { stop = AGATHA_STOP_ZDROP; d_stop = d + 1; } }
+    resolve();
+    sync_state();
+    out_score = st.max; out_qend = st.mq; out_tend = st.mt; out_stop = stop; out_dstop = d_stop;
+    return true;
+}
+
+// Persistent kernel: every group of NW warps pulls alignments from a queue ordered longest-first by the host scheduler.
+template <int C, int NW, int JWS>
+__global__ void __launch_bounds__(Shape16<C, NW>::threads, Shape16<C, NW>::min_blocks) extend16_kernel(JobArrays ja, KernelParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int cta_warp = (int)(threadIdx.x >> 5);
+    const int warp = NW == 1 ? 0 : cta_warp;
+    __shared__ Shared16<C, NW> smem;
+    Shared16<C, NW>* sm = &smem;
+    for (;;) {
+        unsigned job = 0;
+        if (NW == 1) {
+            if (lane == 0) job = atomicAdd(ja.counter, 1u);
+            job = __shfl_sync(FULL, job, 0);
+        } else {
+            __syncthreads();                          // everybody is done with the previous job's shared state
+            if (threadIdx.x == 0) sm->job = atomicAdd(ja.counter, 1u);
+            __syncthreads();
+            job = sm->job;
+        }
+        if (job >= (unsigned)ja.n) break;
+        const unsigned idx = ja.order ? __ldg(ja.order + job) : job;
+
+        Pair pr;
+        pr.qlen = (int)__ldg(ja.qlen + idx);
+        pr.tlen = (int)__ldg(ja.tlen + idx);
+        pr.q = ja.qpk + (__ldg(ja.qoff_w + idx) >> 3);     // offsets are in bases, multiples of 8 (agatha_kernel.h:116-117)
+        pr.t = ja.tpk + (__ldg(ja.toff_w + idx) >> 3);
+        pr.pq = (pr.qlen + 7) >> 3; pr.pt = (pr.tlen + 7) >> 3;        // agatha_kernel.h:120-121
+        pr.qwords = pr.pq; pr.twords = pr.pt;
+        pr.tcols = 8 * pr.pt;
+        pr.total = pr.pq + pr.pt - 1;                                  // :165
+        pr.L = pr.qlen + pr.tlen - 1;                                  // :289
+
+        int score = 0, qend = 0, tend = 0, stop = AGATHA_STOP_END, dstop = 0;
+        bool done = true;
+        if (pr.qlen > 0 && pr.tlen > 0) done = run_pair16<C, NW, JWS>(pr, p, lane, warp, cta_warp, sm, score, qend, tend, stop, dstop);
+        if (lane == 0 && warp == 0) {
+            if (done) {
+                ja.score[idx] = score; ja.qend[idx] = qend; ja.tend[idx] = tend;   // agatha_kernel.h:359-363
+                if (ja.stop) ja.stop[idx] = stop;
+                if (ja.dstop) ja.dstop[idx] = dstop;
+            } else {
+                ja.qend[idx] = REDO_MARK;             // the general kernel, launched next on this stream, takes it from here
+            }
+        }
+    }
+}
+
+}  // namespace agatha

@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "extend_kernel.cuh"
+#include "extend16_kernel.cuh"
 #include "engine_internal.h"
 
 namespace agatha {
@@ -30,8 +31,10 @@ inline bool fast_table_ok(const agatha_params_t* p)
     return p->match >= -128 && p->match <= 127 && p->mismatch >= 1 && p->mismatch <= 128;
 }
 
-// AGATHA_S16 (A/B measurements): "0" disables the 16-bit packed loops, "1" = steady state only, "7" = also
-// the tail (needs a -DAGATHA_TAIL16=1 build). Read once per process; the emulation's tests override it through s16_mode().
+// AGATHA_S16 (A/B measurements): "0" disables every 16-bit packed path, "1" = general kernel only, packed
+// steady state, "2" = general kernel only, packed prologue + steady state (the round-1 default), "7" = also its tail (needs
+// a -DAGATHA_TAIL16=1 build); unset = the packed kernel first, general kernel for what it marks. Read once per process; the
+// emulation's tests override it through s16_mode().
 inline int& s16_mode()
 {
     static int mode = [] {
@@ -118,6 +121,41 @@ inline bool dispatch_variant(const KernelParams& kp, const L& l, int* rc)
         case 3202: *rc = dispatch_c<32, 2>(kp, l); return true;
         case 3204: *rc = dispatch_c<32, 4>(kp, l); return true;
         case 3208: *rc = dispatch_c<32, 8>(kp, l); return true;
+    }
+    return false;
+}
+
+// The packed kernel (extend16_kernel.cuh) covers the band widths 7 (mod 8) from 135 up whose prologue provably stays inside
+// 16 bits (kp.s16 bit 1), with table scoring. It runs first; the general kernel then redoes the pairs it marked.
+inline bool packed_kernel_ok(const KernelParams& kp)
+{
+    const Shape sh = shape_for(kp.W);
+    return sh.C >= 8 && (kp.W & 7) == 7 && (kp.s16 & 2) && !kp.force_generic && s16_mode() < 0;
+}
+
+template <int C, int NW, class L>
+inline int dispatch16_c(const KernelParams& kp, const L& l)
+{
+    if (kp.JW == 7) return l.template run16<C, NW, 7>();
+    if constexpr (C > 15) { if (kp.JW == 15) return l.template run16<C, NW, 15>(); }
+    if constexpr (C > 23) { if (kp.JW == 23) return l.template run16<C, NW, 23>(); }
+    if constexpr (C > 31) { if (kp.JW == 31) return l.template run16<C, NW, 31>(); }
+    return set_error(AGATHA_EUNSUPPORTED, "no packed kernel for band_width %d", kp.W);
+}
+
+template <class L>
+inline bool dispatch16_variant(const KernelParams& kp, const L& l, int* rc)
+{
+    if (!packed_kernel_ok(kp)) return false;
+    const Shape sh = shape_for(kp.W);
+    switch (sh.C * 100 + sh.NW) {
+        case 801: *rc = dispatch16_c<8, 1>(kp, l); return true;
+        case 1601: *rc = dispatch16_c<16, 1>(kp, l); return true;
+        case 2401: *rc = dispatch16_c<24, 1>(kp, l); return true;
+        case 3201: *rc = dispatch16_c<32, 1>(kp, l); return true;
+        case 3202: *rc = dispatch16_c<32, 2>(kp, l); return true;
+        case 3204: *rc = dispatch16_c<32, 4>(kp, l); return true;
+        case 3208: *rc = dispatch16_c<32, 8>(kp, l); return true;
     }
     return false;
 }

@@ -28,6 +28,7 @@ typedef void* cudaStream_t;
 enum { cudaSuccess = 0 };
 
 struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
 struct emu_dim3 { unsigned x, y, z; };
 
 namespace emu {

@@ -116,3 +116,10 @@ def align_pairs(pairs, params, s16_mode=-1, ops=None, bucket=True):
     for k in RESULT_DTYPE.names:
         res[k] = out[k]
     return res
+
+
+def last_redo_count():
+    """Pairs of the last align_pairs() call that the packed kernel handed over to the general kernel."""
+    L = lib()
+    L.emu_last_redo_count.restype = ctypes.c_uint32
+    return int(L.emu_last_redo_count())

@@ -7,6 +7,7 @@
 // (extend_dispatch.h), so the emulation runs exactly the template instance the GPU would run.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdio>
 #include <vector>
 
 #include "cuda_runtime.h"          // the shim in this directory (found first through -I)
@@ -138,11 +139,23 @@ struct EmuLauncher {
         }, &ctx);
         return AGATHA_OK;
     }
+    template <int C, int NW, int JWS> int run16() const
+    {
+        struct Ctx { const JobArrays* ja; const KernelParams* kp; } ctx{&ja, &kp};
+        emu::run_block(Shape16<C, NW>::threads, [](void* a) {
+            Ctx* c = (Ctx*)a;
+            extend16_kernel<C, NW, JWS>(*c->ja, *c->kp);
+        }, &ctx);
+        return AGATHA_OK;
+    }
 };
 
 extern "C" {
 
 const char* emu_last_error(void) { return g_err; }
+
+static uint32_t g_redone = 0;
+uint32_t emu_last_redo_count(void) { return g_redone; }     // pairs the packed kernel handed to the general kernel
 
 void emu_set_s16_mode(int mode) { s16_mode() = mode; }
 
@@ -177,13 +190,21 @@ int emu_extend(const uint32_t* qpk, const uint32_t* tpk, const uint32_t* qoff, c
     KernelParams kp;
     int rc = make_kernel_params(params, &kp);
     if (rc) return rc;
-    unsigned counter = 0;
+    unsigned counter = 0, counter2 = 0;
     JobArrays ja;
     ja.qpk = qpk; ja.tpk = tpk; ja.qoff_w = qoff; ja.toff_w = toff; ja.qlen = qlen; ja.tlen = tlen; ja.order = order;
     ja.score = score; ja.qend = qend; ja.tend = tend; ja.stop = stop; ja.dstop = dstop;
     ja.counter = &counter;
     ja.n = (int)n;
+    ja.redo = 0;
     const EmuLauncher l{ja, kp};
+    if (dispatch16_variant(kp, l, &rc)) {            // same sequence as agatha_extend_device (engine.cu)
+        if (rc) return rc;
+        g_redone = 0;
+        for (uint32_t i = 0; i < n; i++) g_redone += qend[i] == REDO_MARK;
+        ja.counter = &counter2;
+        ja.redo = 1;
+    }
     if (dispatch_variant(kp, l, &rc)) return rc;
     return set_error(AGATHA_EUNSUPPORTED, "no kernel for band_width %d", kp.W);
 }

@@ -33,8 +33,10 @@ def test_emulated_kernel_vs_oracle_every_single_warp_shape(emu, oracle, W):
     _cmp(emu, oracle, make_pairs(9100 + W, 20, max(W, 1), max(3 * W, 10), mixed=True), dict(band_width=W, slice_width=1, z_threshold=30), "rand sw1")
 
 
-@pytest.mark.parametrize("s16", [-1, 0, 1])
+@pytest.mark.parametrize("s16", [-1, 0, 1, 2])
 def test_emulated_default_band_all_packed_modes(emu, oracle, s16):
+    # -1: the packed kernel (extend16_kernel.cuh) first, general kernel for what it marks; 0/1/2: general kernel only, with
+    # its 16-bit loops off / steady state / prologue + steady state
     pairs = make_pairs(77, 10, 1600, 3500, mixed=True) + make_pairs(78, 30, 1, 1500, mixed=True)
     _cmp(emu, oracle, pairs, dict(), "w751", s16)
     _cmp(emu, oracle, pairs[:16], dict(match=2, mismatch=5, gap_open=4, gap_extend=1, z_threshold=50, band_width=759), "w759", s16)
@@ -54,3 +56,35 @@ def test_emulated_edge_cases_and_rare_symbols(emu, oracle):
     _cmp(emu, oracle, make_pairs(300, 40, 100, 800, err=0.1, n_rate=0.05), dict(band_width=63), "nrich")
     _cmp(emu, oracle, make_pairs(302, 40, 100, 800, err=0.1, iupac=True), dict(band_width=63), "iupac")
     _cmp(emu, oracle, make_pairs(303, 20, 100, 800, err=0.1), dict(band_width=63, match=200, mismatch=300), "generic scoring")
+
+
+@pytest.mark.parametrize("W", [135, 255, 511, 751, 1023])
+def test_emulated_packed_kernel_stops_and_hand_over(emu, oracle, W):
+    """The packed kernel on every stop reason (end, Z-drop in prologue / steady state / tail, band exit at slice
+    granularity, wrap-up) and its hand-over: pairs it cannot finish are marked and redone by the general kernel."""
+    from pairgen import make_pair
+    rng = np.random.default_rng(40 + W)
+    pairs = [make_pair(rng, int(rng.integers(2 * W, 4 * W + 600)), err=0.06, skew=int(rng.integers(-2 * W, 3 * W))) for _ in range(10)]   # band exit
+    pairs += [make_pair(rng, int(rng.integers(2 * W, 4 * W + 600)), err=0.08, tail=-1) for _ in range(8)]                               # junk tails
+    pairs += make_pairs(50 + W, 10, W + 40, 3 * W + 500, mixed=True)
+    n_long = len(pairs)
+    pairs += make_pairs(60 + W, 6, 1, W, mixed=True)                     # not longer than the band: general kernel
+    pairs += make_pairs(70 + W, 3, 2 * W, 3 * W, err=0.1, iupac=True)    # symbols outside {A,C,G,T,N}: general kernel
+    for sw, Z in ((1, 30), (3, 400), (7, -1)):
+        _cmp(emu, oracle, pairs, dict(band_width=W, slice_width=sw, z_threshold=Z), "packed")
+        assert 6 <= emu.last_redo_count() <= len(pairs) - n_long + 2, emu.last_redo_count()
+
+
+def test_emulated_packed_kernel_rebase_and_range_bailout(emu, oracle):
+    # long identical pairs: the score climbs past the re-centring threshold (8192) several times; match = 5 makes it fast.
+    rng = np.random.default_rng(9)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    t = acgt[rng.integers(0, 4, 9000)]
+    pairs = [(t.copy(), t.copy()), (t[:7000].copy(), t[:7000].copy())]
+    _cmp(emu, oracle, pairs, dict(band_width=135, match=5, mismatch=4), "rebase")
+    assert emu.last_redo_count() == 0
+    # the same with a multi-warp group: the lane-edge slots in shared memory have to follow the re-basing
+    _cmp(emu, oracle, pairs[1:], dict(band_width=1031, match=5, mismatch=4), "rebase, 2 warps")
+    assert emu.last_redo_count() == 0
+    # scores that cannot stay inside 16 bits between two range checks: the packed kernel hands the pair over
+    _cmp(emu, oracle, pairs[:1], dict(band_width=135, match=100, mismatch=100, z_threshold=-1), "bail-out")
