@@ -20,7 +20,7 @@ CUDA_SOURCES = ["engine.cu", "stream.cu", "extend_inst_c2_c4.cu", "extend_inst_c
                 "extend_inst_wide2.cu", "extend_inst_wide4.cu", "extend_inst_wide8.cu",
                 "extend16_inst_c8_c16.cu", "extend16_inst_c24.cu", "extend16_inst_c32.cu",
                 "extend16_inst_wide2.cu", "extend16_inst_wide4.cu", "extend16_inst_wide8.cu"]
-CXX_SOURCES = ["host_utils.cpp", "fasta.cpp", "synth.cpp", "job.cpp", "gasal_compat.cpp"]   # manual_main.cpp is the driver, linked separately
+CXX_SOURCES = ["host_utils.cpp", "host_pack.cpp", "fasta.cpp", "synth.cpp", "job.cpp", "gasal_compat.cpp"]   # manual_main.cpp is the driver, linked separately
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp,-Wall", "--default-stream", "per-thread"]
 

@@ -134,6 +134,8 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     const int W = p.W;
     const int gl = 32 * warp + lane;
     const bool edge_lane = (gl == p.LW), dead_lane = gl > p.LW;
+    // PRMT selector that replaces the half of register JP holding the cell k = +W (band-edge lane) or nothing (other lanes)
+    const unsigned edge_sel = edge_lane ? (JH ? 0x7610u : 0x3254u) : 0x3210u;
 
     // ---- what this kernel does not handle --------------------------------------------------------------------------
     // first d whose valid k-range is clipped by the far matrix edges (tlen, not tcols: padding columns need the tail's patches)
@@ -379,25 +381,25 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     bool ev_empty = false;
     unsigned vm2 = 0u;                                                   // tail: valid-cell bits of the anti-diagonal being computed
     auto half_mask = [&](int jj) -> unsigned { return (unsigned)imad((int)((vm2 >> jj) & 0x00010001u), p.m16, 0); };
-    // maximum over the group of this lane's value; NW > 1: contains the group's barrier of this anti-diagonal
-    auto group_max = [&](int lane_h, int par) -> int {
-        int h = __reduce_max_sync(FULL, lane_h);
-        if (NW > 1) {
-            if (lane == 0) sm->scan_h[par][warp] = h;
-            __syncthreads();
-            h = __reduce_max_sync(FULL, lane < NW ? sm->scan_h[par][lane] : INT_MIN);
-        }
-        return h;
-    };
     auto owner_warp = [&](int h, int par) -> int {                      // highest warp whose maximum is h (ties -> largest target index)
         if (NW == 1) return 0;
         const unsigned who = __ballot_sync(FULL, lane < NW && sm->scan_h[par][lane < NW ? lane : 0] == h);
         return 31 - __clz((int)who);
     };
+    // The maximum over the warp of both halves of best2 without touching the ALU pipe (which bounds this kernel): one warp
+    // reduction of the packed word yields the largest high half, one of the word shifted left by 16 (FMA pipe) the largest low
+    // half. The lane's own maximum is only needed when something happens.
     auto scan_fast = [&](unsigned best2, const unsigned (&A)[P], int dd, int u, bool tailm) -> bool {   // tailm: constant at every call site
-        const int lane_h = (int)max(best2 & 0xffffu, best2 >> 16);
-        const int h = group_max(lane_h, dd & 1);
+        const unsigned rhi = __reduce_max_sync(FULL, best2);
+        const unsigned rlo = __reduce_max_sync(FULL, (unsigned)imad((int)best2, p.k65536, 0));
+        int h = (int)(max(rhi, rlo) >> 16);
+        if (NW > 1) {
+            if (lane == 0) sm->scan_h[dd & 1][warp] = h;
+            __syncthreads();
+            h = __reduce_max_sync(FULL, lane < NW ? sm->scan_h[dd & 1][lane] : INT_MIN);
+        }
         if ((unsigned)(h - thrS) <= spanS) return false;
+        const int lane_h = (int)max(best2 & 0xffffu, best2 >> 16);
         if (h > maxS) {
             const int ow = owner_warp(h, dd & 1);
             if (NW == 1 || warp == ow) {
@@ -481,7 +483,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             }
             const unsigned ein = prmt(x, AE[P - 1], 0x5432);             // lo: neighbour's E[C-1], hi: own E[P-1]
             best2 = cells16<C, 0, TAILM>(A0, AE, AF, Qw, Rw, ein, k, vm2);
-            if (edge_lane) AE[JP] = JH ? ((AE[JP] & 0xffffu) | (FLOORU16 << 16)) : ((AE[JP] & 0xffff0000u) | FLOORU16);   // nothing leaks into k = W+1
+            AE[JP] = prmt(AE[JP], floor2, edge_sel);                    // band-edge lane: nothing leaks into k = W+1
             if (BLK) shift_ref_blk(); else shift_ref();
             if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }   // inputs of the next anti-diagonal
             if (NW > 1) { if (lane == 0) sm->edgeF[warp] = AF[0]; }
@@ -494,7 +496,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             const unsigned fin = prmt(AF[0], y, 0x5432);                 // lo: own F[P], hi: neighbour's F[0]
             best2 = cells16<C, 1, TAILM>(A1, AE, AF, Qw, Rw, fin, k, vm2);
             // k = +W reads MINUS_INF2 from outside the band; in the prologue that cell is dead until F(0,W) is injected
-            if (!PRO) { if (edge_lane) AF[JP] = JH ? ((AF[JP] & 0xffffu) | ((unsigned)negS << 16)) : ((AF[JP] & 0xffff0000u) | (unsigned)negS); }
+            if (!PRO) AF[JP] = prmt(AF[JP], (unsigned)negS * 0x10001u, edge_sel);
             if (BLK) shift_query_blk(); else shift_query();
             if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }
             if (NW > 1) { if (lane == 31) sm->edgeE[warp] = AE[P - 1]; }

@@ -62,7 +62,7 @@ inline int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
     const unsigned m = (unsigned)p->match & 0xffu, x = (unsigned)(-p->mismatch) & 0xffu;
     kp->tab_lo = m | (x << 8) | (x << 16) | (x << 24);
     kp->tab_hi = 0xffffffffu;
-    kp->one = 1; kp->k32 = 32; kp->m16 = 0xffff;
+    kp->one = 1; kp->k32 = 32; kp->m16 = 0xffff; kp->k65536 = 65536;
     kp->force_generic = fast_table_ok(p) ? 0 : 1;
     // 16-bit packed steady state (extend_kernel.cuh run_fast16): needs small scoring values so that the per-window drift
     // bounds of its range monitor hold

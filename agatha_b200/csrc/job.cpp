@@ -64,23 +64,20 @@ struct JobView {
     int32_t *score, *qend, *tend, *stop, *dstop;
 };
 
-// Stage one batch exactly like gasal_host_batch_fill (host_batch.cpp:79-154): each sequence at a multiple of 8, padded with 'N'.
-int fill_batch(Batch& b, const JobView& jv, int fill_threads, uint64_t& qbytes, uint64_t& tbytes)
+// Stage one batch with gasal_host_batch_fill's layout (host_batch.cpp:79-154: each sequence at a multiple of 8, padded with
+// 'N') but already in the packed device format, per-pair ops applied on the way: half the H2D bytes, no pack kernel.
+int fill_batch(Batch& b, const JobView& jv, int fill_threads, uint64_t& qbases, uint64_t& tbases)
 {
     const uint64_t n = b.ids.size();
     const uint64_t qtot = agatha_staged_bytes(jv.ql, b.ids.data(), n), ttot = agatha_staged_bytes(jv.tl, b.ids.data(), n);
     if (qtot > 0xfffffff8ull || ttot > 0xfffffff8ull) return set_error(AGATHA_EINVAL, "batch exceeds 4 GiB of bases; lower batch_alns");
     int rc = agatha_stream_reserve(b.s, (uint32_t)n, qtot, ttot);
     if (rc) return rc;
-    rc = agatha_stage_batch(jv.qb, jv.qo, jv.ql, b.ids.data(), n, agatha_stream_query_bases(b.s), qtot,
-                            agatha_stream_query_offsets(b.s), agatha_stream_query_lens(b.s), &qbytes, fill_threads);
+    rc = agatha_pack_batch(jv.qb, jv.qo, jv.ql, b.ids.data(), jv.qops, n, 0, agatha_stream_query_packed(b.s), qtot / 8,
+                           agatha_stream_query_offsets(b.s), agatha_stream_query_lens(b.s), &qbases, fill_threads);
     if (rc) return rc;
-    if (jv.qops || jv.tops) {
-        uint8_t *qo = agatha_stream_query_ops(b.s), *to = agatha_stream_target_ops(b.s);
-        for (uint64_t j = 0; j < n; j++) { qo[j] = jv.qops ? jv.qops[b.ids[j]] : 0; to[j] = jv.tops ? jv.tops[b.ids[j]] : 0; }
-    }
-    return agatha_stage_batch(jv.tb, jv.to, jv.tl, b.ids.data(), n, agatha_stream_target_bases(b.s), ttot,
-                              agatha_stream_target_offsets(b.s), agatha_stream_target_lens(b.s), &tbytes, fill_threads);
+    return agatha_pack_batch(jv.tb, jv.to, jv.tl, b.ids.data(), jv.tops, n, 1, agatha_stream_target_packed(b.s), ttot / 8,
+                             agatha_stream_target_offsets(b.s), agatha_stream_target_lens(b.s), &tbases, fill_threads);
 }
 
 void collect(Batch& b, const JobView& jv, Worker& w)
@@ -138,11 +135,10 @@ void run_worker(Worker& w, const JobView& jv, uint32_t batch_alns, int n_streams
         next += cnt;
         uint64_t qbytes = 0, tbytes = 0;
         int rc = fill_batch(b, jv, fill_threads, qbytes, tbytes);
-        if (!rc) rc = (jv.qops || jv.tops) ? agatha_stream_submit_ops(b.s, qbytes, tbytes, (uint32_t)cnt, jv.params)
-                                           : agatha_stream_submit(b.s, qbytes, tbytes, (uint32_t)cnt, jv.params);
+        if (!rc) rc = agatha_stream_submit_packed(b.s, qbytes, tbytes, (uint32_t)cnt, jv.params);
         if (rc) { fail(rc); break; }
         b.busy = true;
-        w.h2d += qbytes + tbytes + 20ull * cnt + ((jv.qops || jv.tops) ? 2ull * cnt : 0);
+        w.h2d += (qbytes + tbytes) / 2 + 20ull * cnt;
         w.batches++;
         cur = (cur + 1) % n_streams;
     }
@@ -153,7 +149,12 @@ void run_worker(Worker& w, const JobView& jv, uint32_t batch_alns, int n_streams
             if (!rc) collect(b, jv, w);
         }
     }
-    for (auto it = bs.rbegin(); it != bs.rend(); ++it) if (it->s) pool_put(w.device, it->s);   // same stream, same slot next time
+    // back to the pool (same stream, same slot next time) -- unless something failed: a stream whose submit or wait failed may
+    // still have copies or kernels in flight on its staging, or be stuck in the "submitted" state; destroy those instead
+    for (auto it = bs.rbegin(); it != bs.rend(); ++it) {
+        if (!it->s) continue;
+        if (w.rc == AGATHA_OK) pool_put(w.device, it->s); else agatha_stream_destroy(it->s);
+    }
 }
 
 }  // namespace

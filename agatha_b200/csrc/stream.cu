@@ -29,7 +29,9 @@ struct agatha_stream {
     // device
     uint8_t *d_q = nullptr, *d_t = nullptr;
     uint32_t *d_qp = nullptr, *d_tp = nullptr;
-    uint64_t dcap_q = 0, dcap_t = 0;
+    uint64_t dcap_q = 0, dcap_t = 0;   // capacity in bases of the packed buffers
+    uint64_t acap_q = 0, acap_t = 0;   // capacity of the ASCII mirrors (0 until an ASCII batch is submitted)
+    bool ascii = false;                // this stream has been used with ASCII batches: keep the mirrors sized
     uint32_t* d_meta = nullptr;
     int32_t* d_res = nullptr;
     uint8_t* d_ops = nullptr;
@@ -88,21 +90,31 @@ void agatha_stream_destroy(agatha_stream_t* s)
     delete s;
 }
 
-static int grow_device(agatha_stream_t* s, uint32_t n, uint64_t qbytes, uint64_t tbytes)
+// Device buffers: the packed words always; the unpacked ASCII mirror (d_q / d_t) only for streams that were actually given
+// an ASCII batch (agatha_stream_submit[_ops]) -- batches packed on the host never need it.
+static int grow_device(agatha_stream_t* s, uint32_t n, uint64_t qbytes, uint64_t tbytes, bool need_ascii)
 {
     if (qbytes > s->dcap_q) {
         const uint64_t cap = std::max<uint64_t>(round_up(qbytes, 4096), s->dcap_q * 2);
-        cudaFree(s->d_q); cudaFree(s->d_qp); s->d_q = nullptr; s->d_qp = nullptr; s->dcap_q = 0;
-        CK(cudaMalloc((void**)&s->d_q, cap), "cudaMalloc(query bases)");
+        cudaFree(s->d_q); cudaFree(s->d_qp); s->d_q = nullptr; s->d_qp = nullptr; s->dcap_q = 0; s->acap_q = 0;
         CK(cudaMalloc((void**)&s->d_qp, cap / 2 + 4 * AGATHA_PACK_SLACK_WORDS), "cudaMalloc(packed query)");
         s->dcap_q = cap;
     }
     if (tbytes > s->dcap_t) {
         const uint64_t cap = std::max<uint64_t>(round_up(tbytes, 4096), s->dcap_t * 2);
-        cudaFree(s->d_t); cudaFree(s->d_tp); s->d_t = nullptr; s->d_tp = nullptr; s->dcap_t = 0;
-        CK(cudaMalloc((void**)&s->d_t, cap), "cudaMalloc(target bases)");
+        cudaFree(s->d_t); cudaFree(s->d_tp); s->d_t = nullptr; s->d_tp = nullptr; s->dcap_t = 0; s->acap_t = 0;
         CK(cudaMalloc((void**)&s->d_tp, cap / 2 + 4 * AGATHA_PACK_SLACK_WORDS), "cudaMalloc(packed target)");
         s->dcap_t = cap;
+    }
+    if (need_ascii && s->acap_q < s->dcap_q) {
+        cudaFree(s->d_q); s->d_q = nullptr; s->acap_q = 0;
+        CK(cudaMalloc((void**)&s->d_q, s->dcap_q), "cudaMalloc(query bases)");
+        s->acap_q = s->dcap_q;
+    }
+    if (need_ascii && s->acap_t < s->dcap_t) {
+        cudaFree(s->d_t); s->d_t = nullptr; s->acap_t = 0;
+        CK(cudaMalloc((void**)&s->d_t, s->dcap_t), "cudaMalloc(target bases)");
+        s->acap_t = s->dcap_t;
     }
     if (n > s->dcap_n) {
         const uint32_t cap = std::max<uint32_t>(n, s->dcap_n * 2);
@@ -148,7 +160,7 @@ int agatha_stream_reserve(agatha_stream_t* s, uint32_t n_alns, uint64_t query_by
     }
     // device side too, so that a submit of anything that fits the reservation never allocates (cudaMalloc/cudaFree
     // synchronise the whole device)
-    return grow_device(s, n_alns, round_up(query_bytes, 8), round_up(target_bytes, 8));
+    return grow_device(s, n_alns, round_up(query_bytes, 8), round_up(target_bytes, 8), s->ascii);
 }
 
 void agatha_stream_capacity(agatha_stream_t* s, uint32_t* max_alns, uint64_t* query_bytes, uint64_t* target_bytes)
@@ -159,6 +171,8 @@ void agatha_stream_capacity(agatha_stream_t* s, uint32_t* max_alns, uint64_t* qu
 }
 uint8_t* agatha_stream_query_bases(agatha_stream_t* s) { return s->h_q; }
 uint8_t* agatha_stream_target_bases(agatha_stream_t* s) { return s->h_t; }
+uint32_t* agatha_stream_query_packed(agatha_stream_t* s) { return (uint32_t*)s->h_q; }
+uint32_t* agatha_stream_target_packed(agatha_stream_t* s) { return (uint32_t*)s->h_t; }
 uint32_t* agatha_stream_query_offsets(agatha_stream_t* s) { return s->h_meta; }
 uint32_t* agatha_stream_target_offsets(agatha_stream_t* s) { return s->h_meta + (size_t)s->cap_n; }
 uint32_t* agatha_stream_query_lens(agatha_stream_t* s) { return s->h_meta + 2 * (size_t)s->cap_n; }
@@ -168,7 +182,7 @@ uint8_t* agatha_stream_target_ops(agatha_stream_t* s) { return s->h_ops + (size_
 
 }  // extern "C"
 
-static int submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns, const agatha_params_t* params, bool with_ops)
+static int submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns, const agatha_params_t* params, bool with_ops, bool packed)
 {
     if (!s) return set_error(AGATHA_EINVAL, "stream is NULL");
     // the reference's argument checks, gasal_align.cu:33-68
@@ -183,7 +197,8 @@ static int submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_byte
     if (s->state == 1) return set_error(AGATHA_EINVAL, "stream busy: poll or wait first");
     if (!params) return set_error(AGATHA_EINVAL, "params is NULL");
     CK(cudaSetDevice(s->device), "cudaSetDevice");
-    int rc = grow_device(s, n_alns, query_bytes, target_bytes);
+    if (!packed) s->ascii = true;
+    int rc = grow_device(s, n_alns, query_bytes, target_bytes, !packed);
     if (rc) return rc;
 
     uint32_t* h_qoff = s->h_meta;
@@ -201,12 +216,17 @@ static int submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_byte
 
     cudaStream_t st = s->st;
     CK(cudaEventRecord(s->ev[0], st), "cudaEventRecord");
-    CK(cudaMemcpyAsync(s->d_q, s->h_q, query_bytes, cudaMemcpyHostToDevice, st), "H2D query bases");
-    CK(cudaMemcpyAsync(s->d_t, s->h_t, target_bytes, cudaMemcpyHostToDevice, st), "H2D target bases");
     for (int k = 0; k < 5; k++)
         CK(cudaMemcpyAsync(s->d_meta + (size_t)k * s->dcap_n, s->h_meta + (size_t)k * s->cap_n, sizeof(uint32_t) * n_alns, cudaMemcpyHostToDevice, st), "H2D batch metadata");
-    if ((rc = agatha_pack_device(s->d_q, query_bytes, s->d_t, target_bytes, s->d_qp, s->d_tp, st))) return rc;
     const size_t dn = s->dcap_n;
+    if (packed) {                                     // packed on the host (agatha_pack_batch): half the bytes, no pack kernel
+        CK(cudaMemcpyAsync(s->d_qp, s->h_q, query_bytes / 2, cudaMemcpyHostToDevice, st), "H2D packed query");
+        CK(cudaMemcpyAsync(s->d_tp, s->h_t, target_bytes / 2, cudaMemcpyHostToDevice, st), "H2D packed target");
+    } else {
+        CK(cudaMemcpyAsync(s->d_q, s->h_q, query_bytes, cudaMemcpyHostToDevice, st), "H2D query bases");
+        CK(cudaMemcpyAsync(s->d_t, s->h_t, target_bytes, cudaMemcpyHostToDevice, st), "H2D target bases");
+        if ((rc = agatha_pack_device(s->d_q, query_bytes, s->d_t, target_bytes, s->d_qp, s->d_tp, st))) return rc;
+    }
     if (with_ops) {                                   // gasal_align.cu:199-212
         for (int k = 0; k < 2; k++)
             CK(cudaMemcpyAsync(s->d_ops + (size_t)k * dn, s->h_ops + (size_t)k * s->cap_n, n_alns, cudaMemcpyHostToDevice, st), "H2D ops");
@@ -230,12 +250,17 @@ extern "C" {
 
 int agatha_stream_submit(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns, const agatha_params_t* params)
 {
-    return submit(s, query_bytes, target_bytes, n_alns, params, false);
+    return submit(s, query_bytes, target_bytes, n_alns, params, false, false);
+}
+
+int agatha_stream_submit_packed(agatha_stream_t* s, uint64_t query_bases, uint64_t target_bases, uint32_t n_alns, const agatha_params_t* params)
+{
+    return submit(s, query_bases, target_bases, n_alns, params, false, true);
 }
 
 int agatha_stream_submit_ops(agatha_stream_t* s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns, const agatha_params_t* params)
 {
-    return submit(s, query_bytes, target_bytes, n_alns, params, true);
+    return submit(s, query_bytes, target_bytes, n_alns, params, true, false);
 }
 
 static void finish(agatha_stream_t* s)

@@ -254,3 +254,22 @@ def stage_batch(buf, off, lens, ids=None, n_threads=0):
                                _ptr(dst, u8p), ctypes.c_uint64(need), _ptr(doff, u32p), _ptr(dlen, u32p), ctypes.byref(nbytes),
                                ctypes.c_int32(n_threads)))
     return dst[:int(nbytes.value)], doff, dlen
+
+
+def pack_batch(buf, off, lens, is_target, ids=None, ops=None, n_threads=0):
+    """agatha_pack_batch: unpadded ASCII sequences -> the packed device format (8 bases per uint32 word) with the reference's
+    batch layout (each sequence at a multiple of 8 bases, 'N' padded), ops applied. Returns (words, offsets in bases, lens)."""
+    buf = _a(buf, np.uint8); off = _a(off, np.uint64); lens = _a(lens, np.uint32)
+    idp = _a(ids, np.uint64) if ids is not None else None
+    opp = _a(ops, np.uint8) if ops is not None else None
+    n = len(idp) if idp is not None else len(lens)
+    L = lib()
+    L.agatha_staged_bytes.restype = ctypes.c_uint64
+    need = int(L.agatha_staged_bytes(_ptr(lens, u32p), _ptr(idp, u64p), ctypes.c_uint64(n)))
+    dst = np.empty(need // 8, np.uint32)
+    doff = np.empty(n, np.uint32); dlen = np.empty(n, np.uint32)
+    nb = ctypes.c_uint64(0)
+    check(L.agatha_pack_batch(_ptr(buf, u8p), _ptr(off, u64p), _ptr(lens, u32p), _ptr(idp, u64p), _ptr(opp, u8p), ctypes.c_uint64(n),
+                              ctypes.c_int32(1 if is_target else 0), _ptr(dst, u32p), ctypes.c_uint64(len(dst)),
+                              _ptr(doff, u32p), _ptr(dlen, u32p), ctypes.byref(nb), ctypes.c_int32(n_threads)))
+    return dst[:int(nb.value) // 8], doff, dlen

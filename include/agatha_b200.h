@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AGATHA_B200_ABI_VERSION 1
+#define AGATHA_B200_ABI_VERSION 2
 
 enum {
     AGATHA_OK = 0,
@@ -133,6 +133,11 @@ uint32_t *agatha_stream_target_lens(agatha_stream_t *s);
 uint8_t *agatha_stream_query_ops(agatha_stream_t *s);
 uint8_t *agatha_stream_target_ops(agatha_stream_t *s);
 
+/* Pinned staging for batches that are packed on the host (agatha_pack_batch): the same buffers seen as 32-bit words,
+ * capacity = reserved bytes / 4 words each. */
+uint32_t *agatha_stream_query_packed(agatha_stream_t *s);
+uint32_t *agatha_stream_target_packed(agatha_stream_t *s);
+
 /* Asynchronous: H2D of the staged batch, pack, length-aware bucketing, extension kernel, D2H of the results.
  * query_bytes/target_bytes > 0 and multiples of 8, n_alns > 0 (gasal_align.cu:33-68). */
 int agatha_stream_submit(agatha_stream_t *s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns,
@@ -140,6 +145,11 @@ int agatha_stream_submit(agatha_stream_t *s, uint64_t query_bytes, uint64_t targ
 /* Same, with the staged op bytes applied between packing and alignment (the reference's isReverseComplement path). */
 int agatha_stream_submit_ops(agatha_stream_t *s, uint64_t query_bytes, uint64_t target_bytes, uint32_t n_alns,
                              const agatha_params_t *params);
+/* Same for a batch staged in packed form (agatha_stream_*_packed() filled by agatha_pack_batch): query_bases / target_bases
+ * are the staged BASES (multiples of 8), half as many bytes are uploaded and no pack kernel runs. Ops, if any, were
+ * applied by agatha_pack_batch. */
+int agatha_stream_submit_packed(agatha_stream_t *s, uint64_t query_bases, uint64_t target_bases, uint32_t n_alns,
+                                const agatha_params_t *params);
 /* 0 = finished (results valid until the next submit), -1 = still running, -2 = nothing submitted
  * (the three return values of gasal_is_aln_async_done, gasal_align.cu:276-292). */
 int agatha_stream_poll(agatha_stream_t *s);
@@ -211,6 +221,17 @@ int agatha_stage_batch(const uint8_t *bases, const uint64_t *offsets, const uint
                        int32_t n_threads);
 /* Bytes agatha_stage_batch will need. */
 uint64_t agatha_staged_bytes(const uint32_t *lens, const uint64_t *ids, uint64_t n);
+
+/* The same staging, but straight into the packed device format (8 bases per 32-bit word, the library's private 4-bit codes):
+ * host_batch.cpp:79-154 and the pack kernel (kernels/pack_rc_seqs.h:13-53) in one pass over the bases, so that only half the
+ * bytes cross PCIe and nothing is packed on the device. is_target selects the target word layout (first base in the bottom
+ * nibble; queries carry it in the top nibble). ops (optional, indexed like lens) applies reverse (bit 0) / complement
+ * (bit 1) to a sequence on the way, as gasal_reversecomplement_kernel would (pack_rc_seqs.h:56-212). dst_offsets are in BASES
+ * (multiples of 8; word index = offset / 8), *bases_out = staged bases (a multiple of 8): the values agatha_stream_submit_packed
+ * and agatha_extend_device expect. dst_words may be pinned staging from agatha_stream_*_packed(). */
+int agatha_pack_batch(const uint8_t *bases, const uint64_t *offsets, const uint32_t *lens, const uint64_t *ids, const uint8_t *ops,
+                      uint64_t n, int32_t is_target, uint32_t *dst_words, uint64_t dst_capacity_words,
+                      uint32_t *dst_offsets, uint32_t *dst_lens, uint64_t *bases_out, int32_t n_threads);
 
 /* FASTA reader for the reference's input format: records ">>> idx" + sequence lines, both files read in
  * lock-step (test_prog.cpp:94-149). Returns an opaque handle or NULL. */

@@ -175,3 +175,34 @@ dist.destroy_process_group()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_host_packer_matches_the_device_pack_kernels(ag):
+    """agatha_pack_batch (host, AVX2 + scalar) writes exactly the words pack_kernel + apply_ops_kernel write on the device --
+    checked here against those kernels run by the SIMT emulation (tests/emu), including ops, ragged lengths, IUPAC codes,
+    lower case, empty sequences and a sub-selection through ids."""
+    from emu import emu
+    L = emu.lib()
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTNacgtnRYKMSWBDHVU-", dtype=np.uint8)
+    lens = np.array([0, 1, 7, 8, 9, 31, 32, 33, 63, 64, 65, 100, 257, 1000, 4097] + list(rng.integers(0, 300, 40)), dtype=np.uint32)
+    seqs = [alphabet[rng.integers(0, 5 if i % 3 else len(alphabet), int(n))] for i, n in enumerate(lens)]
+    buf = np.concatenate(seqs) if lens.sum() else np.zeros(1, np.uint8)
+    off = np.zeros(len(lens), np.uint64); off[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+    ops = rng.integers(0, 4, len(lens)).astype(np.uint8)
+    ids = rng.permutation(len(lens))[:40].astype(np.uint64)
+    for target in (False, True):
+        for use_ops in (False, True):
+            words, doff, dlen = ag.host_api.pack_batch(buf, off, lens, target, ids=ids, ops=ops if use_ops else None, n_threads=3)
+            # the device path: stage as ASCII, pack_kernel, then apply_ops_kernel
+            staged, soff, slen = ag.stage_batch(buf, off, lens, ids=ids)
+            assert (soff == doff).all() and (slen == dlen).all() and len(words) == len(staged) // 8
+            qp = np.zeros(len(staged) // 8 + 64, np.uint32); tp = np.zeros(len(staged) // 8 + 64, np.uint32)
+            p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+            L.emu_pack(p(staged), ctypes.c_uint64(len(staged)), p(staged), ctypes.c_uint64(len(staged)), p(qp), p(tp))
+            if use_ops:
+                o = np.ascontiguousarray(ops[ids.astype(np.int64)])
+                L.emu_apply_ops(p(staged), p(staged), p(soff), p(soff), p(slen), p(slen), p(o), p(o), ctypes.c_uint32(len(ids)), p(qp), p(tp))
+            ref = (tp if target else qp)[:len(words)]
+            bad = np.nonzero(ref != words)[0]
+            assert len(bad) == 0, (target, use_ops, bad[:5], [hex(int(x)) for x in ref[bad[:3]]], [hex(int(x)) for x in words[bad[:3]]])
