@@ -15,12 +15,13 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libagatha_b200.so")
 STAMP = os.path.join(LIBDIR, "libagatha_b200.stamp")
+SYNTH_LIB = os.path.join(LIBDIR, "libagatha_synth.so")
 
 CUDA_SOURCES = ["engine.cu", "stream.cu", "extend_inst_c2_c4.cu", "extend_inst_c8_c16.cu", "extend_inst_c24.cu", "extend_inst_c32.cu",
                 "extend_inst_wide2.cu", "extend_inst_wide4.cu", "extend_inst_wide8.cu",
                 "extend16_inst_c8_c16.cu", "extend16_inst_c24.cu", "extend16_inst_c32.cu",
                 "extend16_inst_wide2.cu", "extend16_inst_wide4.cu", "extend16_inst_wide8.cu"]
-CXX_SOURCES = ["host_utils.cpp", "host_pack.cpp", "fasta.cpp", "synth.cpp", "job.cpp", "gasal_compat.cpp"]   # manual_main.cpp is the driver, linked separately
+CXX_SOURCES = ["host_utils.cpp", "host_pack.cpp", "fasta.cpp", "job.cpp", "gasal_compat.cpp"]   # manual_main.cpp is the driver, linked separately
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp,-Wall", "--default-stream", "per-thread"]
 
@@ -39,6 +40,7 @@ def _sources():
 def _digest():
     h = hashlib.sha256()
     files = sorted([os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h"))])
+    files += [os.path.join(ROOT, "tools", "synth", f) for f in ("synth.cpp", "agatha_synth.h")]
     for dp, _, fns in sorted(os.walk(os.path.join(ROOT, "include"))):
         files += [os.path.join(dp, f) for f in sorted(fns)]
     for f in files:
@@ -52,7 +54,7 @@ def _digest():
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+    if not force and os.path.exists(LIB) and os.path.exists(SYNTH_LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
     objs = []
     procs = []
@@ -83,6 +85,12 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("driver link failed:\n" + r.stdout)
+    # bench / test tooling: the synthetic workload generator, deliberately NOT part of the product library
+    synth = os.path.join(ROOT, "tools", "synth")
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fopenmp", "-I" + synth, os.path.join(synth, "synth.cpp"), "-o", SYNTH_LIB]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("synth build failed:\n" + r.stdout)
     with open(STAMP, "w") as f:
         f.write(dig)
     return LIB

@@ -8,7 +8,19 @@
 // Layout: cells are addressed by anti-diagonal d = q + r and diagonal k = r - q; global lane gl of a
 // group of NW warps owns the cells k = -W + 2*(C*gl + j) + u, j in [0,C), u in {0,1}. Register jj of each state array holds
 // cell jj in its low half and cell jj + C/2 in its high half, as UNSIGNED biased 16-bit numbers relative to a per-alignment
-// base, so VIADDMNMX.U16x2 / VIMNMX3.U16x2 update two cells per instruction and t = M - goe is one IMAD on the FMA pipe.
+// base, so VIADDMNMX.U16x2 / VIMNMX3.U16x2 update two cells per instruction.
+//
+// Drifting representation. ncu shows the ALU pipe at 92 % of its peak in this kernel and the FMA pipe at 14 %, so every
+// operation that can be an IMAD should be one. M = H(d-2) + s is an IMAD when no half can borrow, i.e. when the score is
+// never negative: the table holds s + X (X = mismatch penalty: 0 for a mismatch, match + X for a match, X - 1 against N)
+// and the surplus is absorbed by the representation itself -- a value of anti-diagonal d is stored with the offset
+//     off(d) = bias - base + D(d),   D(d) = X * (d >> 1) + (d odd ? X/2 : 0)
+// so that H(d-2) + (s + X) is already in the units of anti-diagonal d. E and F are produced in the units of the NEXT
+// anti-diagonal (their VIADDMNMX adds delta(d) - ge, the IMAD for t adds delta(d) - goe, delta(d) = D(d+1) - D(d)), and the
+// thresholds of the Z-drop scan advance by delta per step. Stored H never decreases along a diagonal, so the low end of the
+// 16-bit window needs no monitoring between re-basings; the drift (X/2 per anti-diagonal) is taken out by the re-basing
+// that the growing score needs anyway. MINUS_INF2 outside the band is the stored floor: the range monitor hands a pair to
+// the general kernel before a live value could get as low as -16384 + goe, so the exact value of the sentinel never matters.
 // What differs from the packed loops inside extend_kernel (run_fast16):
 //   * no 32-bit state at all: half the live registers, no conversion code, no spills;
 //   * the anti-diagonal that holds the running maximum is snapshotted to SHARED memory (3-4 STS.128 per lane) instead of
@@ -48,15 +60,16 @@ struct Shape16 {
 // Scoring and recurrence constants of one alignment, held in plain registers: ptxas otherwise re-materialises them from the
 // constant bank inside the hot loop (12 moves per two anti-diagonals for the PRMT table alone).
 struct Consts16 {
-    unsigned tab_lo, tab_hi;   // PRMT lookup table: byte x -> score for code XOR x
-    unsigned mge2;             // -ge in both halves (two's complement)
-    int mgoe32;                // subtracts goe from both halves at once
-    int one;                   // 1, opaque to ptxas: keeps t = M*1 - goe on the FMA pipe
+    unsigned tab_lo, tab_hi;   // PRMT lookup table: byte x -> score + X for code XOR x (never negative)
+    unsigned ce[2];            // by parity U: delta - ge in both halves (two's complement), the addend of the E/F extension
+    int ct[2];                 // by parity U: (delta - goe) * 0x10001, the addend of t = M - goe
+    int one;                   // 1, opaque to ptxas: keeps a*1 + c on the FMA pipe (IMAD) instead of the ALU pipe (IADD3)
     int m16;                   // 0xffff, opaque too: (bit pair) * 0xffff widens a valid-cell bit to a 16-bit mask on the FMA pipe
 };
 
-// One anti-diagonal step for the C cells of parity U owned by this lane, on packed state (see step_cells16 in
-// extend_kernel.cuh for the representation). Recurrence: CORE_COMPUTE, agatha_kernel.h:20-30 (gap opens from M = diag + s).
+// One anti-diagonal step for the C cells of parity U owned by this lane, on packed state in the drifting representation
+// (file header). Recurrence: CORE_COMPUTE, agatha_kernel.h:20-30 (gap opens from M = diag + s). Per register (two cells):
+// ALU pipe PRMT (score pair), VIMNMX3 (H), 2 x VIADDMNMX (E, F), 1/2 VIMNMX3 (maximum); FMA pipe 2 x IMAD (M, t).
 // TAILM: `vm2` holds one bit per cell of this anti-diagonal that lies inside the matrix (cells 0..P-1 in bits 0.., cells
 // P..C-1 in bits 16..); the others still take part in the recurrence (nothing inside the matrix ever reads them) but are
 // kept out of the maximum. Returns the packed maximum of H.
@@ -66,7 +79,6 @@ __device__ __forceinline__ unsigned cells16(unsigned (&H)[C / 2], unsigned (&E)[
                                             unsigned edge_in, const Consts16& k, unsigned vm2)
 {
     constexpr int P = C / 2, NWORD = C / 8;
-    const unsigned floor2 = FLOORU16 * 0x10001u;
     unsigned sc[2 * NWORD];
 #pragma unroll
     for (int w = 0; w < NWORD; w++) {
@@ -75,22 +87,25 @@ __device__ __forceinline__ unsigned cells16(unsigned (&H)[C / 2], unsigned (&E)[
         sc[2 * w + 1] = prmt(k.tab_lo, k.tab_hi, x >> 16);
     }
     unsigned best = 0u, pend = 0u;
+    unsigned oE[P], oF[P];                                     // inputs of this step (the outputs of the previous one)
+#pragma unroll
+    for (int jj = 0; jj < P; jj++) { oE[jj] = E[jj]; oF[jj] = F[jj]; }
 #pragma unroll
     for (int t_ = 0; t_ < P; t_++) {
-        const int jj = (U == 0) ? (P - 1 - t_) : t_;          // U == 0 reads E[j-1] (old) -> walk downwards; U == 1 reads F[j+1] -> upwards
+        const int jj = t_;
         unsigned ein, fin;
-        if (U == 0) { ein = (jj == 0) ? edge_in : E[jj - 1]; fin = F[jj]; }
-        else        { ein = E[jj]; fin = (jj == P - 1) ? edge_in : F[jj + 1]; }
-        // sign-extended score pair: byte (a&3) of sc[a>>2] for cell a = jj, byte (b&3) of sc[b>>2] for cell b = jj + P
+        if (U == 0) { ein = (jj == 0) ? edge_in : oE[jj - 1]; fin = oF[jj]; }
+        else        { ein = oE[jj]; fin = (jj == P - 1) ? edge_in : oF[jj + 1]; }
+        // zero-extended score pair: byte (a&3) of sc[a>>2] for cell a = jj, byte (b&3) of sc[b>>2] for cell b = jj + P
+        // (selector nibbles 1 and 3 replicate the sign of a byte that is never negative: zero)
         const int a = jj, b = jj + P;
         const unsigned sel = (unsigned)(a & 3) | ((unsigned)((a & 3) | 8) << 4) | ((unsigned)(4 + (b & 3)) << 8) | ((unsigned)((4 + (b & 3)) | 8) << 12);
         const unsigned s2 = prmt(sc[a >> 2], sc[b >> 2], sel);
-        const unsigned m = __viaddmax_u16x2(H[jj], s2, floor2);           // max(H(d-2,k) + s, FLOOR)
-        // (t before h: h can then take over m's register instead of being moved into place afterwards)
-        const unsigned t = (unsigned)imad((int)m, k.one, k.mgoe32);        // M - goe in both halves: no borrow, m >= FLOORU16 > goe
+        const unsigned m = (unsigned)imad((int)H[jj], k.one, (int)s2);       // H(d-2,k) + s + X: no half can carry or borrow
+        const unsigned t = (unsigned)imad((int)m, k.one, k.ct[U]);           // M - goe, in the units of the next anti-diagonal
         const unsigned h = __vimax3_u16x2(m, ein, fin);
-        E[jj] = __viaddmax_u16x2(ein, k.mge2, t);
-        F[jj] = __viaddmax_u16x2(fin, k.mge2, t);
+        E[jj] = __viaddmax_u16x2(ein, k.ce[U], t);
+        F[jj] = __viaddmax_u16x2(fin, k.ce[U], t);
         H[jj] = h;
         unsigned hm = h;
         if (TAILM) hm = h & (unsigned)imad((int)((vm2 >> jj) & 0x00010001u), k.m16, 0);
@@ -101,6 +116,28 @@ __device__ __forceinline__ unsigned cells16(unsigned (&H)[C / 2], unsigned (&E)[
     }
     if (P & 1) best = __vimax3_u16x2(best, pend, pend);
     return best;
+}
+
+// Symbols the packed kernel scores: query {A,C,G,T}, target {A,C,G,T,N} (codes 0..3 and TCODE_N, which the windows hold as
+// TCODE_N & 7 = 5 so that every code XOR stays below 8 and indexes the table directly). Anything else -- including an N in
+// the read -- goes to the general kernel.
+__device__ __forceinline__ bool outside_packed_alphabet(const Pair& pr, int lane)
+{
+    bool rare = false;
+    for (int i = lane; i < pr.qwords; i += 32) {
+        const uint32_t w = __ldg(pr.q + i);
+        const bool last = (i == pr.qwords - 1);                            // the last word carries the 'N' padding (QCODE_N = 4)
+        const uint32_t keep = last ? (0xffffffffu << (4 * ((8 - (pr.qlen & 7)) & 7))) : 0xffffffffu;   // first base in the top nibble
+        rare |= (w & keep & 0xccccccccu) != 0u;
+    }
+    for (int i = lane; i < pr.twords; i += 32) {
+        const uint32_t w = __ldg(pr.t + i);
+        const uint32_t hi = (w | (w >> 1)) & 0x44444444u;                 // bit2 set <=> nibble >= 4 (bit3|bit2)
+        const uint32_t x = w ^ 0xddddddddu;                               // nibble == 0 <=> code 13
+        const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;   // 1 <=> nibble != 13
+        rare |= ((hi >> 2) & nz) != 0u;
+    }
+    return __any_sync(FULL, rare);
 }
 
 template <int C, int NW>
@@ -142,14 +179,19 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     const int d_tail = min(2 * pr.qlen - 2 - W, 2 * pr.tlen - 2 - W) + 1;
     const int d_fast_hi = min(d_tail - 1, pr.L - 1) & ~1;
     if (W + 1 >= d_fast_hi) return false;                               // pair not longer than the band: general kernel
-    if (has_rare_symbols(pr, lane)) return false;                      // PRMT table scores {A,C,G,T,N} only
+    if (outside_packed_alphabet(pr, lane)) return false;
 
     // ---- state -----------------------------------------------------------------------------------------------------------
-    const unsigned floor2 = pack16(FLOOR16, FLOOR16);
+    const unsigned floor2 = FLOORU16 * 0x10001u;
+    const int X = p.mismatch;                                            // surplus of the biased scores, absorbed by the drift
+    const int de = X >> 1, dod = X - de;                                 // delta(d) for even / odd d
+    auto D = [&](int dd) { return X * (dd >> 1) + ((dd & 1) ? de : 0); };   // cumulative drift (arithmetic shift: D(-2) = -X)
+    const int bias = p.bias16;                                           // stored = true - base + bias + D(d)
+    auto pk = [&](int v) { return ((unsigned)v & 0xffffu) * 0x10001u; };   // a stored value in both halves
     Consts16 k;
-    k.tab_lo = p.tab_lo; k.tab_hi = p.tab_hi;
-    k.mge2 = pack16raw(-p.ge, -p.ge);
-    k.mgoe32 = -(int)((unsigned)p.goe | ((unsigned)p.goe << 16));
+    k.tab_lo = p.tabb_lo; k.tab_hi = p.tabb_hi;
+    k.ce[1] = pack16raw(de - p.ge, de - p.ge);   k.ct[1] = (de - p.goe) * 0x10001;      // parity 1 <-> even d
+    k.ce[0] = pack16raw(dod - p.ge, dod - p.ge); k.ct[0] = (dod - p.goe) * 0x10001;
     k.one = p.one; k.m16 = p.m16;
     {
         // ptxas keeps warp-uniform values in uniform registers and copies them into a vector register in front of every PRMT
@@ -161,7 +203,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     unsigned A0[P], A1[P], AE[P], AF[P];
 #pragma unroll
     for (int jj = 0; jj < P; jj++) { A0[jj] = floor2; A1[jj] = floor2; AE[jj] = floor2; AF[jj] = floor2; }
-    int base = 0;                                                        // packed value = true value - base (+ BIAS16 as stored)
+    int base = 0;                                                        // re-basing so far (stored = true - base + bias + D(d))
 
     // sequence windows at d = 0: nibble j <-> query[qtop - j], target[rbot + j]
     int qtop = (W >> 1) - C * gl;
@@ -171,7 +213,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     for (int w = 0; w < NWORD; w++) { Qw[w] = 0u; Rw[w] = 0u; }
 #pragma unroll 1
     for (int j = 0; j < C; j++) {
-        const unsigned qb = qbase(pr, qtop - j) << (4 * (j & 7)), tb = tbase(pr, rbot + j) << (4 * (j & 7));
+        const unsigned qb = qbase(pr, qtop - j) << (4 * (j & 7)), tb = (tbase(pr, rbot + j) & 7u) << (4 * (j & 7));
 #pragma unroll
         for (int w = 0; w < NWORD; w++) if (w == (j >> 3)) { Qw[w] |= qb; Rw[w] |= tb; }
     }
@@ -179,7 +221,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     auto refeed = [&]() {                                // feeds for the generic (one base at a time) window shifts
         const int nq = qtop + 1, nb = rbot + C;
         qfeed = load_qword(pr, nq >> 3) << (4 * (nq & 7));
-        rfeed = load_tword(pr, nb >> 3) >> (4 * (nb & 7));
+        rfeed = (load_tword(pr, nb >> 3) & 0x77777777u) >> (4 * (nb & 7));
     };
     refeed();
     auto shift_query = [&]() {                           // qtop -> qtop + 1
@@ -193,7 +235,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     };
     auto shift_ref = [&]() {                             // rbot -> rbot + 1
         const int nb = rbot + C;
-        if ((nb & 7) == 0) rfeed = load_tword(pr, nb >> 3);
+        if ((nb & 7) == 0) rfeed = load_tword(pr, nb >> 3) & 0x77777777u;
 #pragma unroll
         for (int w = 0; w < NWORD - 1; w++) Rw[w] = __funnelshift_r(Rw[w], Rw[w + 1], 4);
         Rw[NWORD - 1] = __funnelshift_r(Rw[NWORD - 1], rfeed, 4);
@@ -228,39 +270,38 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
 
     // ---- boundary: H(-1,-1) = 0 and the virtual cells of "anti-diagonal -1" (agatha_kernel.h:126-148) -------------------
     {
-        const int hv = -p.goe, gv = hv - p.goe;                       // H(-1,0) = H(0,-1) = -goe; F(0,0) = E(0,0) = that - goe
-        poke16(A1, own(W >> 1), pack16(0, 0));                       // k = 0 belongs to parity 1 (W odd)
+        // H(-1,-1) = 0 is read as the diagonal of step 0 (units of anti-diagonal -2); H(-1,0) = H(0,-1) = -goe as diagonals of
+        // step 1 (units of -1); F(0,0) = E(0,0) = -2 goe as gap inputs of step 0 (units of 0)
+        const int hv = -p.goe + bias + D(-1), gv = -2 * p.goe + bias + D(0);
+        poke16(A1, own(W >> 1), pk(0 + bias + D(-2)));                 // k = 0 belongs to parity 1 (W odd)
         const int jt = own((W + 1) >> 1);                              // top: (q=-1, r=0) at k = 1
-        poke16(A0, jt, pack16(hv, hv)); poke16(AF, jt, pack16(gv, gv));
+        poke16(A0, jt, pk(hv)); poke16(AF, jt, pk(gv));
         const int jl = own((W - 1) >> 1);                              // left: (q=0, r=-1) at k = -1
-        poke16(A0, jl, pack16(hv, hv)); poke16(AE, jl, pack16(gv, gv));
+        poke16(A0, jl, pk(hv)); poke16(AE, jl, pk(gv));
     }
 
     ScanState st = {0, 0, 0, scan_threshold(0, p)};                    // agatha_kernel.h:158-161
     int stop = AGATHA_STOP_END, d_stop = pr.L;
     const bool has_phantom = pr.tcols > pr.tlen;
 
-    // Everything the hot loops compare against lives in the STORED domain (true - base + BIAS16), as ints.
-    // The running maximum lives in the STORED domain while the loops run (maxS = st.max - base + BIAS16); st.max / st.thr are
-    // brought up to date only where the cold paths need them. thrS = maxS - Z (or -1 when Z-drop is off; gap_extend < 0 never
-    // gets here), so thrS <= maxS and "nothing can happen on this anti-diagonal" (thrS <= h <= maxS) is ONE unsigned
-    // comparison: h - thrS <= spanS, with spanS = Z a constant of the launch (or maxS + 1).
-    const bool zoff = p.Z < 0;
-    int maxS, thrS;
-    unsigned spanS;
-    auto set_max = [&](int hS) {                                       // hot: a new maximum hS (stored domain)
-        maxS = hS;
-        thrS = zoff ? -1 : hS - p.Z;
-        spanS = zoff ? (unsigned)(hS + 1) : (unsigned)p.Z;
-    };
-    auto sync_state = [&]() { st.max = maxS - BIAS16 + base; st.thr = scan_threshold(st.max, p); };   // cold: before scan_update / output
-    set_max(0 - base + BIAS16);
-    int negS = max(NEG16 - base, FLOOR16) + BIAS16;                    // MINUS_INF2 as stored
-    // Between two range checks (32 anti-diagonals) the smallest live H falls by at most 16*mismatch and the largest rises by
-    // at most 16*match; M = H + s and t = M - goe must stay above the clamp, H + match below the top. Dead (out-of-band)
-    // cells creep upwards by `match` on equal bases: they are pushed back to the floor at every range check.
-    const int low_ok = FLOOR16 + 17 * max(max(p.mismatch, p.match), 1) + p.goe + 64 + BIAS16;
-    const int high_ok = TOP16 - 17 * max(p.match, 0) - 64 + BIAS16;
+    // Z-drop scan state of the hot loops, in the STORED units of the anti-diagonal being computed: thrS = (running maximum)
+    // - Z, advanced by delta at the start of every step. "Nothing can happen on this anti-diagonal" (thr <= h <= max) is ONE
+    // unsigned comparison, h - thrS <= Z (Z-drop off: Z = 2^30, so only a new maximum can fail it). The maximum itself is
+    // kept as (mx_h, mx_d): its stored value and the anti-diagonal whose units that value is in; st.max / st.thr are brought
+    // up to date only where the cold paths need them.
+    const int Zeff = p.Z < 0 ? (1 << 30) : p.Z;
+    int mx_h = bias + D(0), mx_d = 0;                                    // true 0 (agatha_kernel.h:158)
+    int thrS = mx_h - Zeff - dod;                                        // step 0 adds delta(-1) = dod first
+    auto sync_state = [&]() { st.max = mx_h - bias + base - D(mx_d); st.thr = scan_threshold(st.max, p); };   // cold: before scan_update / output
+    // Range monitor (every 32 anti-diagonals). Stored H never decreases along a diagonal, so the low end only moves when the
+    // state is re-based; low_ok keeps t = M - goe + delta free of borrows and the floor below every live candidate. At the top
+    // a live value rises by at most (match + X) per two anti-diagonals. neg_ok: the lowest TRUE live value for which
+    // MINUS_INF2 (-16384) outside the band still loses every maximum it enters during the next 34 anti-diagonals.
+    // Dead (out-of-band) cells creep upwards from the floor by at most (match + X) per two anti-diagonals between two checks
+    // (they are pushed back at every check) and must stay below every live value: hence the 17 * (match + X).
+    const int low_ok = (int)FLOORU16 + 17 * (max(p.match, 0) + X) + p.goe + 2 * p.ge + 64;
+    const int high_ok = 65535 - 17 * (max(p.match, 0) + X) - 64;
+    const int neg_ok = NEG16 + p.goe + p.ge + 17 * X + 64;
 
     // ---- snapshot of the anti-diagonal that holds the running maximum (shared memory) ------------------------------------
     int snap_d = -1, snap_u = 0, snap_src = 0, snap_w = 0, snap_h = 0;
@@ -312,7 +353,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     };
 
     // ---- range monitor over the live H values (both parities) + re-basing; false = values leave the safe window --------
-    auto check_range = [&]() -> bool {
+    auto check_range = [&](int d_now) -> bool {                         // d_now: the anti-diagonal about to be computed
         // push the dead positions back to the floor (lanes beyond the band; in the band-edge lane the cells beyond k = +W)
 #pragma unroll
         for (int jj = 0; jj < P; jj++) {
@@ -342,27 +383,24 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             mx = __reduce_max_sync(FULL, lane < NW ? sm->rng[1][lane] : 0);
             __syncthreads();
         }
-        if (mn < low_ok || mx > high_ok) return false;
-        if (mx > 8192 + BIAS16) {                                        // re-centre: rare (every ~8192 score units)
-            const int delta = min(mx - BIAS16, mn - low_ok);
+        if (mn < low_ok) return false;
+        if (mn - bias + base - D(d_now) < neg_ok) return false;          // MINUS_INF2 could matter soon: general kernel
+        if (mx > high_ok - 1024) {                                       // re-base: bring the lowest live value down to low_ok
+            const int delta = mn - low_ok;
+            if (mx - delta > high_ok) return false;                      // live values span more than the window
             if (delta > 0) {
-                // the packed add does not saturate: lift everything to FLOOR16 + delta first, then subtract
-                const unsigned md2 = pack16raw(-delta, -delta), lift2 = pack16(FLOOR16 + delta, FLOOR16 + delta);
+                // the packed add does not saturate: lift everything to the floor + delta first, then subtract
+                const unsigned md2 = pack16raw(-delta, -delta), lift2 = pk((int)FLOORU16 + delta);
                 auto shift_down = [&](unsigned x) { return __viaddmax_u16x2(__vimax3_u16x2(x, lift2, lift2), md2, floor2); };
 #pragma unroll
                 for (int jj = 0; jj < P; jj++) {
                     A0[jj] = shift_down(A0[jj]); A1[jj] = shift_down(A1[jj]); AE[jj] = shift_down(AE[jj]); AF[jj] = shift_down(AF[jj]);
                 }
-                if (snap_d >= 0) {                                       // the snapshot is compared with stored values: move it along
-                    if (NW == 1 || warp == snap_w) {
-#pragma unroll
-                        for (int jj = 0; jj < P; jj++) sm->snap[cta_warp][jj][lane] = shift_down(sm->snap[cta_warp][jj][lane]);
-                    }
-                    snap_h -= delta;
-                }
+                // (the snapshot and snap_h stay in the units they were taken in: they are only ever compared with each other,
+                // and with the drift a snapshot that followed every re-basing would sink below the floor)
                 base += delta;
-                negS = max(NEG16 - base, FLOOR16) + BIAS16;
-                set_max(maxS - delta);
+                mx_h -= delta;
+                thrS -= delta;
             }
         }
         if (NW > 1) {
@@ -398,9 +436,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             __syncthreads();
             h = __reduce_max_sync(FULL, lane < NW ? sm->scan_h[dd & 1][lane] : INT_MIN);
         }
-        if ((unsigned)(h - thrS) <= spanS) return false;
+        if ((unsigned)(h - thrS) <= (unsigned)Zeff) return false;
         const int lane_h = (int)max(best2 & 0xffffu, best2 >> 16);
-        if (h > maxS) {
+        if (h > thrS) {                                                  // above the window: a new maximum
             const int ow = owner_warp(h, dd & 1);
             if (NW == 1 || warp == ow) {
                 const unsigned who = __ballot_sync(FULL, lane_h == h);
@@ -408,7 +446,8 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
                 snapshot(A, vm2, tailm);
             }
             snap_d = dd; snap_u = u; snap_w = ow; snap_h = h;
-            set_max(h);
+            mx_h = h; mx_d = dd;
+            thrS = h - Zeff;
             return false;
         }
         ev_lane_h = lane_h; ev_h = h;
@@ -430,7 +469,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             g = C * (32 * warp + src) + jb;
         }
         g = group_bcast(g, ow);
-        return scan_update(st, ev_h - BIAS16 + base, g, dd, u, p);
+        return scan_update(st, ev_h - bias + base - D(dd), g, dd, u, p);
     };
 
     // phantom (padding) target columns: their F and diagonal inputs restart from MINUS_INF2 at the first row of every slice
@@ -442,7 +481,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         if (!(qc == 0 || ((qc >> 3) + pr.pt - 1) % p.sw == 0)) return;
         const int r = dn - qc, k = r - qc;
         if (k > W || k < -W) return;
-        const unsigned v2 = (unsigned)negS * 0x10001u;
+        const unsigned v2 = floor2;                                      // MINUS_INF2 (file header)
         const int g = (k + W - U) >> 1;
         const int gf = (U == 0) ? g : g + 1;                             // its F input: U==0 reads F[j], U==1 reads F[j+1]
         poke16(AF, own(gf), v2);
@@ -458,6 +497,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         constexpr int MODE = decltype(mode_tag)::value;
         constexpr bool PRO = MODE == 1, TAILM = MODE == 2, BLK = decltype(blk_tag)::value != 0;
         using UN = std::integral_constant<int, 1 - U>;
+        thrS += (U == 1) ? dod : de;                                     // into the units of this anti-diagonal: delta(dd - 1)
         bool empty = false;
         if (TAILM) {
             // cells of this anti-diagonal inside the matrix (padding columns count: agatha_kernel.h CORE_COMPUTE has no r < tlen guard)
@@ -477,8 +517,8 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
                 if (NW == 1 || warp == 0) {
                     // left of k = -W: MINUS_INF2; in the prologue the cell is not real yet (dead), and on d == W its left
                     // neighbour is the matrix-edge value E(W,0) (agatha_kernel.h:130)
-                    if (!PRO) x = (unsigned)negS << 16;
-                    else x = (unsigned)(((dd == W) ? (-(p.goe + p.ge * W) - p.goe - base) : FLOOR16) + BIAS16) << 16;
+                    if (!PRO) x = FLOORU16 << 16;
+                    else x = (unsigned)((dd == W) ? (-(p.goe + p.ge * W) - p.goe + bias + D(W)) : (int)FLOORU16) << 16;
                 } else x = sm->edgeE[warp - 1];
             }
             const unsigned ein = prmt(x, AE[P - 1], 0x5432);             // lo: neighbour's E[C-1], hi: own E[P-1]
@@ -496,7 +536,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             const unsigned fin = prmt(AF[0], y, 0x5432);                 // lo: own F[P], hi: neighbour's F[0]
             best2 = cells16<C, 1, TAILM>(A1, AE, AF, Qw, Rw, fin, k, vm2);
             // k = +W reads MINUS_INF2 from outside the band; in the prologue that cell is dead until F(0,W) is injected
-            if (!PRO) AF[JP] = prmt(AF[JP], (unsigned)negS * 0x10001u, edge_sel);
+            if (!PRO) AF[JP] = prmt(AF[JP], floor2, edge_sel);
             if (BLK) shift_query_blk(); else shift_query();
             if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }
             if (NW > 1) { if (lane == 31) sm->edgeE[warp] = AE[P - 1]; }
@@ -534,8 +574,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         constexpr int U = decltype(u_tag)::value, S = decltype(s_tag)::value;
         constexpr bool EVEN = (U == 1);
         constexpr int PT = EVEN ? S : ((S + 1) & 3), PL = (2 - S) & 3;
-        const int hv = -(p.goe + p.ge * (dd + 1)) - base, gv = hv - p.goe;
-        const unsigned hv2 = pack16(hv, hv), gv2 = pack16(gv, gv);
+        // H of the virtual cells in the units of anti-diagonal dd, their E / F in the units of dd + 1 (base is 0 in the prologue)
+        const int hv = -(p.goe + p.ge * (dd + 1)), gv = hv - p.goe;
+        const unsigned hv2 = pk(hv + bias + D(dd)), gv2 = pk(gv + bias + D(dd + 1));
         const bool h_top = !(EVEN && S == 3 && blk_last);                 // d + 2 > W: only F is needed
 #pragma unroll
         for (int R = 0; R < NGH; R++) {
@@ -607,7 +648,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     if (!fired) {
         // ---- steady state: blocks of 16 anti-diagonals, range check every second block --------------------------------------
         while (d + 16 <= d_fast_hi && !fired && !redo) {
-            if (d - d_check >= 32) { if (!check_range()) { redo = true; break; } d_check = d; }
+            if (d - d_check >= 32) { if (!check_range(d)) { redo = true; break; } d_check = d; }
             {
                 // feeds of the block: 8 query bases (first in the top nibble) and 8 target bases (first in the bottom nibble)
                 window_pos(d);
@@ -615,7 +656,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
                 const uint32_t q0 = load_qword(pr, nq >> 3), q1 = load_qword(pr, (nq >> 3) + 1);
                 const uint32_t t0 = load_tword(pr, nb >> 3), t1 = load_tword(pr, (nb >> 3) + 1);
                 qfeed = __funnelshift_l(q1, q0, 4 * (nq & 7));
-                rfeed = __funnelshift_r(t0, t1, 4 * (nb & 7));
+                rfeed = __funnelshift_r(t0, t1, 4 * (nb & 7)) & 0x77777777u;
             }
             const int dblk = d + 16;
 #if AGATHA_INLINE_EVENTS
@@ -660,7 +701,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         int next_slice = ((d + span - 1) / span) * span;
         if (has_phantom) phantom_patch16(d, U1{});                       // inputs of the first tail step
         while (d < d_end && !fired && !redo && !band_exit) {
-            if (d - d_check >= 32) { if (!check_range()) { redo = true; break; } d_check = d; }
+            if (d - d_check >= 32) { if (!check_range(d)) { redo = true; break; } d_check = d; }
             const int dchunk = min(d_end, d_check + 32);
             int ev = 0;
 #pragma unroll 1

@@ -83,6 +83,27 @@ inline int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
         // (C1: 21.2 -> 27.0 ms, ncu: no_instruction 1.6 -> 2.9 warps per issue).
         if (mode == 7) kp->s16 |= 4;
     }
+    // The packed kernel (extend16_kernel.cuh, drifting representation). Table of biased scores s + X, X = mismatch: match + X,
+    // 0, X - 1 (N_PENALTY = 1, gasal_kernels.h:48-50) -- all must fit a non-negative byte. bias16 places the prologue inside
+    // the 16-bit window: on its anti-diagonals a live true value is at least -lowtrue (two gaps from the origin plus the
+    // mismatches of at most half a band), a dead cell creeps up from the floor by at most `creep`, a live value rises to at
+    // most (match + X) * half in stored units.
+    kp->p16_ok = 0; kp->bias16 = 0; kp->tabb_lo = kp->tabb_hi = 0;
+    if ((kp->s16 & 1) && p->mismatch >= 1 && p->match >= 0 && p->match + p->mismatch <= 127 && (p->band_width & 7) == 7) {
+        const long long X = p->mismatch, half = (p->band_width + 2) / 2;
+        const long long creep = (p->match + X) * half;
+        const long long lowtrue = 3LL * kp->goe + (long long)kp->ge * (p->band_width + 2) + X * half + 128;
+        const long long bias = 4000 /* FLOORU16 */ + creep + lowtrue + kp->goe + 2LL * kp->ge + 17 * (p->match + X) + 320;
+        const bool fits = bias + creep + 2048 < 65535 - 17 * (p->match + X);
+        // (MINUS_INF2 is not read during the prologue -- the band edges are still outside the matrix -- and the range check
+        // that follows it tests the lowest live value against the sentinel before the steady state uses it)
+        if (fits) {
+            kp->p16_ok = 1; kp->bias16 = (int)bias;
+            const unsigned m = (unsigned)(p->match + X), n = (unsigned)(X - 1);
+            kp->tabb_lo = m;                                    // x = 0 match, 1..3 mismatch (0)
+            kp->tabb_hi = n | (n << 8) | (n << 16) | (n << 24);  // x = 4..7: a base against N
+        }
+    }
     return AGATHA_OK;
 }
 
@@ -130,7 +151,7 @@ inline bool dispatch_variant(const KernelParams& kp, const L& l, int* rc)
 inline bool packed_kernel_ok(const KernelParams& kp)
 {
     const Shape sh = shape_for(kp.W);
-    return sh.C >= 8 && (kp.W & 7) == 7 && (kp.s16 & 2) && !kp.force_generic && s16_mode() < 0;
+    return sh.C >= 8 && kp.p16_ok && !kp.force_generic && s16_mode() < 0;
 }
 
 template <int C, int NW, class L>

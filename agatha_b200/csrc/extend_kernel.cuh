@@ -47,6 +47,10 @@ struct KernelParams {
     int one, k32;                    // the constants 1 and 32, opaque to ptxas: keep a*1+c and h*32+j on IMAD (FMA pipe)
     int m16;                         // 0xffff, opaque too: (bit pair) * 0xffff widens a valid-cell bit to a 16-bit mask on the FMA pipe
     int k65536;                      // 65536, opaque: x * 65536 is a shift by 16 on the FMA pipe
+    // packed kernel (extend16_kernel.cuh): table of the biased scores s + mismatch, initial offset of the stored values
+    unsigned tabb_lo, tabb_hi;
+    int bias16;
+    int p16_ok;                      // the packed kernel's preconditions hold for these parameters
     int s16;                         // bit 0: steady state, bit 1: prologue, bit 2: tail may run on 16-bit packed state (engine.cu)
     int force_generic;               // match/mismatch do not fit the byte table: score every pair with compare/select
 };

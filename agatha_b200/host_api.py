@@ -35,20 +35,37 @@ def device_count():
     return int(lib().agatha_device_count())
 
 
+_synth = None
+
+
+def _synth_lib():
+    """libagatha_synth.so: the workload generator is bench / test tooling and lives outside the product library."""
+    global _synth
+    if _synth is None:
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libagatha_synth.so")
+        if not os.path.exists(path):
+            raise AgathaError("libagatha_synth.so not found: run `python -m agatha_b200.build`")
+        _synth = ctypes.CDLL(path)
+    return _synth
+
+
 def synth_pairs(profile, seed, n_pairs, first_pair=0, n_threads=0):
     """Deterministic synthetic pairs: profile 1=C1, 2=ONT-like, 3=HiFi-like, 4=heavy tail.
     Returns dict(qbuf, qoff, qlen, tbuf, toff, tlen): ASCII bases, byte offsets (uint64), lengths (uint32)."""
-    L = lib()
+    L = _synth_lib()
     n = int(n_pairs)
     qlen = np.zeros(n, np.uint32); tlen = np.zeros(n, np.uint32)
     qoff = np.zeros(n, np.uint64); toff = np.zeros(n, np.uint64)
     args = lambda qb, qc, tb, tc: (ctypes.c_int32(profile), ctypes.c_uint64(seed), ctypes.c_uint64(first_pair), ctypes.c_uint64(n),
                                    _ptr(qlen, u32p), _ptr(tlen, u32p), _ptr(qoff, u64p), _ptr(toff, u64p),
                                    qb, ctypes.c_uint64(qc), tb, ctypes.c_uint64(tc), ctypes.c_int32(n_threads))
-    check(L.agatha_synth_pairs(*args(None, 0, None, 0)))
+    if L.agatha_synth_pairs(*args(None, 0, None, 0)) != 0:
+        raise AgathaError("agatha_synth_pairs: bad arguments")
     qtot = int(qlen.sum(dtype=np.uint64)); ttot = int(tlen.sum(dtype=np.uint64))
     qbuf = np.empty(max(qtot, 1), np.uint8); tbuf = np.empty(max(ttot, 1), np.uint8)
-    check(L.agatha_synth_pairs(*args(_ptr(qbuf, u8p), qtot, _ptr(tbuf, u8p), ttot)))
+    if L.agatha_synth_pairs(*args(_ptr(qbuf, u8p), qtot, _ptr(tbuf, u8p), ttot)) != 0:
+        raise AgathaError("agatha_synth_pairs failed")
     return dict(qbuf=qbuf, qoff=qoff, qlen=qlen, tbuf=tbuf, toff=toff, tlen=tlen)
 
 

@@ -249,14 +249,6 @@ const uint32_t *agatha_fasta_target_lens(const agatha_fasta_pairs_t *f);
 const uint8_t *agatha_fasta_query_ops(const agatha_fasta_pairs_t *f);   /* header char -> 0..3 (test_prog.cpp:83-92) */
 const uint8_t *agatha_fasta_target_ops(const agatha_fasta_pairs_t *f);
 
-/* Deterministic synthetic read/reference pairs. profile: 1 = C1, 2 = ONT-like, 3 = HiFi-like,
- * 4 = heavy tail with early Z-drop. Two passes: sizes first (bases == NULL), then fill. Offsets in bytes, no padding. */
-int agatha_synth_pairs(int32_t profile, uint64_t seed, uint64_t first_pair, uint64_t n_pairs,
-                       uint32_t *query_lens, uint32_t *target_lens,
-                       uint64_t *query_offsets, uint64_t *target_offsets,
-                       uint8_t *query_bases, uint64_t query_capacity,
-                       uint8_t *target_bases, uint64_t target_capacity, int32_t n_threads);
-
 #ifdef __cplusplus
 }
 #endif

@@ -123,3 +123,8 @@ def last_redo_count():
     L = lib()
     L.emu_last_redo_count.restype = ctypes.c_uint32
     return int(L.emu_last_redo_count())
+
+
+def last_used_packed():
+    """True when the last align_pairs() call ran the packed kernel (extend16_kernel.cuh) before the general one."""
+    return bool(lib().emu_last_used_packed())

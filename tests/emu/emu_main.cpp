@@ -155,7 +155,9 @@ extern "C" {
 const char* emu_last_error(void) { return g_err; }
 
 static uint32_t g_redone = 0;
+static int g_used16 = 0;
 uint32_t emu_last_redo_count(void) { return g_redone; }     // pairs the packed kernel handed to the general kernel
+int emu_last_used_packed(void) { return g_used16; }          // 1 when the last emu_extend ran the packed kernel first
 
 void emu_set_s16_mode(int mode) { s16_mode() = mode; }
 
@@ -198,9 +200,10 @@ int emu_extend(const uint32_t* qpk, const uint32_t* tpk, const uint32_t* qoff, c
     ja.n = (int)n;
     ja.redo = 0;
     const EmuLauncher l{ja, kp};
+    g_used16 = 0; g_redone = 0;
     if (dispatch16_variant(kp, l, &rc)) {            // same sequence as agatha_extend_device (engine.cu)
         if (rc) return rc;
-        g_redone = 0;
+        g_used16 = 1;
         for (uint32_t i = 0; i < n; i++) g_redone += qend[i] == REDO_MARK;
         ja.counter = &counter2;
         ja.redo = 1;

@@ -46,6 +46,9 @@ def test_emulated_default_band_all_packed_modes(emu, oracle, s16):
 def test_emulated_wide_bands_multi_warp_groups(emu, oracle, W, hi):
     pairs = make_pairs(9700 + W, 6, 1, hi, mixed=True) + make_pairs(9800 + W, 2, hi, hi + 300, err=0.01)
     _cmp(emu, oracle, pairs, dict(band_width=W), "wide")
+    assert emu.last_used_packed() == (W % 8 == 7)            # the packed kernel covers W = 7 (mod 8); the general kernel the rest
+    _cmp(emu, oracle, pairs, dict(band_width=W), "wide, general kernel only", s16=2)
+    assert not emu.last_used_packed()
 
 
 def test_emulated_edge_cases_and_rare_symbols(emu, oracle):
@@ -72,7 +75,10 @@ def test_emulated_packed_kernel_stops_and_hand_over(emu, oracle, W):
     pairs += make_pairs(70 + W, 3, 2 * W, 3 * W, err=0.1, iupac=True)    # symbols outside {A,C,G,T,N}: general kernel
     for sw, Z in ((1, 30), (3, 400), (7, -1)):
         _cmp(emu, oracle, pairs, dict(band_width=W, slice_width=sw, z_threshold=Z), "packed")
-        assert 6 <= emu.last_redo_count() <= len(pairs) - n_long + 2, emu.last_redo_count()
+        assert emu.last_used_packed()
+        # handed over: the 9 short / IUPAC pairs for certain, plus the mixed pairs that happen to carry an N in the read
+        n_query_n = sum(1 for q, _ in pairs[:n_long] if (np.asarray(q) == ord("N")).any())
+        assert 6 <= emu.last_redo_count() <= len(pairs) - n_long + n_query_n, emu.last_redo_count()
 
 
 def test_emulated_packed_kernel_rebase_and_range_bailout(emu, oracle):
@@ -86,5 +92,15 @@ def test_emulated_packed_kernel_rebase_and_range_bailout(emu, oracle):
     # the same with a multi-warp group: the lane-edge slots in shared memory have to follow the re-basing
     _cmp(emu, oracle, pairs[1:], dict(band_width=1031, match=5, mismatch=4), "rebase, 2 warps")
     assert emu.last_redo_count() == 0
-    # scores that cannot stay inside 16 bits between two range checks: the packed kernel hands the pair over
-    _cmp(emu, oracle, pairs[:1], dict(band_width=135, match=100, mismatch=100, z_threshold=-1), "bail-out")
+    # the failure of the first drifting build: a maximum early in a long diverged pair (Z-drop practically off), its snapshot
+    # must survive the many re-basings that follow
+    _cmp(emu, oracle, make_pairs(74, 3, 7000, 9000, err=0.3), dict(match=2, mismatch=9, gap_open=12, gap_extend=3, band_width=511, z_threshold=30000), "old snapshot")
+    assert emu.last_used_packed() and emu.last_redo_count() == 0
+    # scoring the packed kernel does not take (biased table entries must fit a byte): general kernel
+    _cmp(emu, oracle, pairs[:1], dict(band_width=135, match=100, mismatch=100, z_threshold=-1), "not eligible")
+    assert not emu.last_used_packed()
+    # Z-drop off on junk: true scores sink towards MINUS_INF2 and the packed kernel hands the pair over before the exact
+    # value of the sentinel could matter
+    junk = [(acgt[rng.integers(0, 4, 12000)], acgt[rng.integers(0, 4, 12000)])]
+    _cmp(emu, oracle, junk, dict(band_width=135, z_threshold=-1), "sinking scores")
+    assert emu.last_used_packed() and emu.last_redo_count() == 1

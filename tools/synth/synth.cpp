@@ -1,3 +1,4 @@
+// BENCH / TEST TOOLING, not part of the product library: builds into agatha_b200/lib/libagatha_synth.so (agatha_b200/build.py).
 // Deterministic synthetic read/reference pairs for the workloads of BASELINE.md section 2.3 (C1..C4).
 // Every pair is generated from hash(seed, pair index) alone, so any shard of any size reproduces the same pairs
 // (the multi-GPU bench generates each rank's shard independently). No GPU needed.
@@ -10,8 +11,7 @@
 #include <omp.h>
 #endif
 
-#include "agatha_b200.h"
-#include "engine_internal.h"
+#include "agatha_synth.h"
 
 namespace {
 
@@ -107,9 +107,9 @@ extern "C" int agatha_synth_pairs(int32_t profile, uint64_t seed, uint64_t first
                                   uint8_t* query_bases, uint64_t query_capacity, uint8_t* target_bases, uint64_t target_capacity,
                                   int32_t n_threads)
 {
-    using namespace agatha;
-    if (profile < 1 || profile > 4) return set_error(AGATHA_EINVAL, "profile must be 1..4");
-    if (!query_lens || !target_lens) return set_error(AGATHA_EINVAL, "NULL length arrays");
+
+    if (profile < 1 || profile > 4) return -1;   // profile must be 1..4
+    if (!query_lens || !target_lens) return -1;
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #else
@@ -122,18 +122,18 @@ extern "C" int agatha_synth_pairs(int32_t profile, uint64_t seed, uint64_t first
             uint64_t qo = 0, to = 0;
             for (uint64_t i = 0; i < n_pairs; i++) { query_offsets[i] = qo; target_offsets[i] = to; qo += query_lens[i]; to += target_lens[i]; }
         }
-        return AGATHA_OK;
+        return 0;
     }
-    if (!query_offsets || !target_offsets) return set_error(AGATHA_EINVAL, "NULL offset arrays");
+    if (!query_offsets || !target_offsets) return -1;
     if (n_pairs) {
         const uint64_t last = n_pairs - 1;
         if (query_offsets[last] + query_lens[last] > query_capacity || target_offsets[last] + target_lens[last] > target_capacity)
-            return set_error(AGATHA_EINVAL, "base buffers too small");
+            return -2;   // base buffers too small
     }
 #pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads)
     for (int64_t i = 0; i < (int64_t)n_pairs; i++) {
         uint32_t ql, tl;
         gen_pair(profile, seed, first_pair + (uint64_t)i, query_bases + query_offsets[i], target_bases + target_offsets[i], ql, tl);
     }
-    return AGATHA_OK;
+    return 0;
 }
