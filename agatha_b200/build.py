@@ -17,7 +17,7 @@ LIB = os.path.join(LIBDIR, "libagatha_b200.so")
 STAMP = os.path.join(LIBDIR, "libagatha_b200.stamp")
 SYNTH_LIB = os.path.join(LIBDIR, "libagatha_synth.so")
 
-CUDA_SOURCES = ["engine.cu", "stream.cu", "extend_inst_c2_c4.cu", "extend_inst_c8_c16.cu", "extend_inst_c24.cu", "extend_inst_c32.cu",
+CUDA_SOURCES = ["engine.cu", "stream.cu", "int_peak.cu", "extend_inst_c2_c4.cu", "extend_inst_c8_c16.cu", "extend_inst_c24.cu", "extend_inst_c32.cu",
                 "extend_inst_wide2.cu", "extend_inst_wide4.cu", "extend_inst_wide8.cu",
                 "extend16_inst_c8_c16.cu", "extend16_inst_c24.cu", "extend16_inst_c32.cu",
                 "extend16_inst_wide2.cu", "extend16_inst_wide4.cu", "extend16_inst_wide8.cu"]

@@ -5,7 +5,10 @@
 //   * a line whose first character is one of "></+" in BOTH files starts a record (the character encodes the -- unused --
 //     reverse/complement op, test_prog.cpp:83-92); every other line is appended to the current record of its file;
 //   * reading stops at the end of the shorter file; a sequence line before the first header is an error (test_prog.cpp:137).
-// Like std::getline, a trailing '\r' is NOT stripped. No GPU needed.
+// Like std::getline, a trailing '\r' is NOT stripped. One deliberate difference: an EMPTY line in both files is skipped here,
+// while the reference takes it for a record header (its strchr("></+", line[0]) also matches the terminating NUL of an
+// empty string, test_prog.cpp:103-106) and then starts an empty record. Records longer than 4 GiB are refused (lengths
+// are 32-bit throughout the API). No GPU needed.
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -133,15 +136,18 @@ agatha_fasta_pairs_t* agatha_fasta_load(const char* query_path, const char* targ
     auto* f = new agatha_fasta_pairs();
     const size_t n = hdr.size();
     f->ql.resize(n); f->tl.resize(n); f->qo.resize(n); f->to.resize(n); f->qop.resize(n); f->top.resize(n);
-#pragma omp parallel for schedule(static) num_threads(threads)
+    bool too_long = false;                      // lengths are 32-bit throughout the ABI (gasal.h:120-123): refuse, never truncate
+#pragma omp parallel for schedule(static) num_threads(threads) reduction(|| : too_long)
     for (int64_t r = 0; r < (int64_t)n; r++) {
         const size_t b = hdr[(size_t)r] + 1, e = ((size_t)r + 1 < n) ? hdr[(size_t)r + 1] : nlines;
         uint64_t a = 0, c = 0;
         for (size_t i = b; i < e; i++) { a += line_len(fq, lq, i); c += line_len(ft, lt, i); }
+        too_long = too_long || a > 0xffffffffull || c > 0xffffffffull;
         f->ql[(size_t)r] = (uint32_t)a; f->tl[(size_t)r] = (uint32_t)c;
         f->qop[(size_t)r] = (uint8_t)op_of(fq.p[lq[hdr[(size_t)r]]]);
         f->top[(size_t)r] = (uint8_t)op_of(ft.p[lt[hdr[(size_t)r]]]);
     }
+    if (too_long) { delete f; set_error(AGATHA_EINVAL, "a record is longer than 4 GiB"); return nullptr; }
     uint64_t qo = 0, to = 0;
     uint32_t mx = 0;
     for (size_t r = 0; r < n; r++) {

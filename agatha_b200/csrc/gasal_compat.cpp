@@ -290,6 +290,55 @@ gasal_res_t* gasal_res_new_host(uint32_t max_n_alns, Parameters*)
     return r;
 }
 
+// Device-side result triples (res.cpp:30-82, :97-115). The engine keeps its own result arrays inside the stream object, so
+// nothing in this library needs these; they are exported, with the reference's behaviour, for callers that manage device
+// results themselves (start fields NULL as in res.cpp:76-77).
+gasal_res_t* gasal_res_new_device_cpy(uint32_t max_n_alns, Parameters*)
+{
+    gasal_res_t* r = (gasal_res_t*)calloc(1, sizeof(gasal_res_t));
+    cudaError_t err;
+    CHECKCUDAERROR(cudaMalloc((void**)&r->aln_score, max_n_alns * sizeof(int32_t)));
+    CHECKCUDAERROR(cudaMalloc((void**)&r->query_batch_end, max_n_alns * sizeof(int32_t)));
+    CHECKCUDAERROR(cudaMalloc((void**)&r->target_batch_end, max_n_alns * sizeof(int32_t)));
+    return r;
+}
+
+gasal_res_t* gasal_res_new_device(gasal_res_t* device_cpy)
+{
+    gasal_res_t* d_c = nullptr;
+    cudaError_t err;
+    CHECKCUDAERROR(cudaMalloc((void**)&d_c, sizeof(gasal_res_t)));
+    CHECKCUDAERROR(cudaMemcpy(d_c, device_cpy, sizeof(gasal_res_t), cudaMemcpyHostToDevice));   // the pointers ARE device pointers
+    return d_c;
+}
+
+void gasal_res_destroy_device(gasal_res_t* device_res, gasal_res_t* device_cpy)
+{
+    if (device_cpy) {
+        if (device_cpy->aln_score) cudaFree(device_cpy->aln_score);
+        if (device_cpy->query_batch_start) cudaFree(device_cpy->query_batch_start);
+        if (device_cpy->target_batch_start) cudaFree(device_cpy->target_batch_start);
+        if (device_cpy->query_batch_end) cudaFree(device_cpy->query_batch_end);
+        if (device_cpy->target_batch_end) cudaFree(device_cpy->target_batch_end);
+        free(device_cpy);
+    }
+    if (device_res) cudaFree(device_res);
+}
+
+// ctors.h:9-11. The reference (re)allocates the unpacked and packed device batches of a storage here (ctors.cpp:178-226);
+// in this library they belong to the stream object, which grows on demand: alloc = reserve, free = nothing to do until
+// gasal_destroy_streams.
+void gasal_gpu_mem_alloc(gasal_gpu_storage_t* g, int gpu_max_query_batch_bytes, int gpu_max_target_batch_bytes, Parameters*)
+{
+    if (gpu_max_query_batch_bytes % 8 || gpu_max_target_batch_bytes % 8) { fprintf(stderr, "[GASAL ERROR:] batch bytes must be multiples of 8\n"); exit(EXIT_FAILURE); }
+    if (agatha_stream_reserve(handle(g), g->host_max_n_alns, (uint64_t)gpu_max_query_batch_bytes, (uint64_t)gpu_max_target_batch_bytes)) die("gasal_gpu_mem_alloc");
+    g->gpu_max_query_batch_bytes = (uint32_t)gpu_max_query_batch_bytes;
+    g->gpu_max_target_batch_bytes = (uint32_t)gpu_max_target_batch_bytes;
+    refresh_views(g);
+}
+
+void gasal_gpu_mem_free(gasal_gpu_storage_t*, Parameters*) {}
+
 void gasal_res_destroy_host(gasal_res_t* r)
 {
     if (!r) return;

@@ -234,3 +234,49 @@ extern "C" int agatha_align_job(const uint8_t* query_bases, const uint64_t* quer
     }
     return AGATHA_OK;
 }
+
+// Start positions (gasal_res_t.query_batch_start / target_batch_start, gasal.h:89-90; the reference allocates neither,
+// res.cpp:27-28, so there is nothing to be bit-compatible with -- the convention is GASAL2's WITH_START, gasal.h:36-39):
+// the start of the best-scoring alignment that ENDS in the reported end cell, found by a second extension that runs
+// backwards from that cell over the reversed prefixes query[0..qend], target[0..tend] -- same scoring and band, Z-drop off.
+// The reverse pass is an ordinary job: the host packer reverses the truncated sequences on the way into pinned staging.
+extern "C" int agatha_align_job_starts(const uint8_t* query_bases, const uint64_t* query_offsets, const uint32_t* query_lens,
+                                       const uint8_t* target_bases, const uint64_t* target_offsets, const uint32_t* target_lens,
+                                       uint64_t n_alns, const agatha_params_t* params, const agatha_job_config_t* cfg,
+                                       int32_t* score, int32_t* query_end, int32_t* target_end, int32_t* stop, int32_t* dstop,
+                                       int32_t* query_start, int32_t* target_start, agatha_job_stats_t* stats)
+{
+    if (!query_start || !target_start) return set_error(AGATHA_EINVAL, "NULL start arrays");
+    if (cfg && (cfg->query_ops || cfg->target_ops)) return set_error(AGATHA_EUNSUPPORTED, "start positions with per-pair ops are not supported");
+    int rc = agatha_align_job(query_bases, query_offsets, query_lens, target_bases, target_offsets, target_lens, n_alns, params, cfg,
+                              score, query_end, target_end, stop, dstop, stats);
+    if (rc || n_alns == 0) return rc;
+    std::vector<uint32_t> ql(n_alns), tl(n_alns);
+    std::vector<uint8_t> rev(n_alns, 1);                                // op bit 0: reverse
+    std::vector<int32_t> s2(n_alns), q2(n_alns), t2(n_alns);
+    for (uint64_t i = 0; i < n_alns; i++) {
+        // empty pairs and pairs without a positive cell report (0, 0, 0): their alignment is empty, the start is the origin
+        const bool none = query_lens[i] == 0 || target_lens[i] == 0;
+        ql[i] = none ? 0u : (uint32_t)query_end[i] + 1u;
+        tl[i] = none ? 0u : (uint32_t)target_end[i] + 1u;
+    }
+    agatha_params_t p2 = *params;
+    p2.z_threshold = -1;
+    agatha_job_config_t c2;
+    if (cfg) c2 = *cfg; else std::memset(&c2, 0, sizeof(c2));
+    c2.query_ops = rev.data(); c2.target_ops = rev.data();
+    agatha_job_stats_t st2;
+    rc = agatha_align_job(query_bases, query_offsets, ql.data(), target_bases, target_offsets, tl.data(), n_alns, &p2, &c2,
+                          s2.data(), q2.data(), t2.data(), nullptr, nullptr, &st2);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n_alns; i++) {
+        const bool none = ql[i] == 0 || tl[i] == 0 || score[i] <= 0;
+        query_start[i] = none ? 0 : query_end[i] - q2[i];
+        target_start[i] = none ? 0 : target_end[i] - t2[i];
+    }
+    if (stats) {
+        stats->seconds_total += st2.seconds_total; stats->seconds_kernel_max += st2.seconds_kernel_max;
+        stats->h2d_bytes += st2.h2d_bytes; stats->d2h_bytes += st2.d2h_bytes; stats->n_batches += st2.n_batches;
+    }
+    return AGATHA_OK;
+}

@@ -25,6 +25,13 @@ def launch_count():
     return int(lib().agatha_launch_count())
 
 
+def measure_int_peak(device=0):
+    """agatha_measure_int_peak: dict(alu, fma, mixed) in 1e12 lane-operations/s, measured now on `device`."""
+    a, f, m = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+    check(lib().agatha_measure_int_peak(ctypes.c_int(device), ctypes.byref(a), ctypes.byref(f), ctypes.byref(m)))
+    return dict(alu=a.value, fma=f.value, mixed=m.value)
+
+
 def stage_pairs(pairs):
     """Host staging exactly like gasal_host_batch_fill (host_batch.cpp:79-154): every sequence is copied to an
     offset that is a multiple of 8 and padded to a multiple of 8 with 'N'. Returns numpy arrays

@@ -171,6 +171,33 @@ def align_job(qbuf, qoff, qlen, tbuf, toff, tlen, params, devices=None, n_device
     return out, stats
 
 
+def align_job_starts(qbuf, qoff, qlen, tbuf, toff, tlen, params, devices=None, batch_alns=0):
+    """agatha_align_job_starts: results of align_job plus (query_start, target_start) int32 arrays (GASAL2's WITH_START
+    convention: start of the best alignment that ends in the reported end cell)."""
+    qbuf, tbuf = _a(qbuf, np.uint8), _a(tbuf, np.uint8)
+    qoff, toff = _a(qoff, np.uint64), _a(toff, np.uint64)
+    qlen, tlen = _a(qlen, np.uint32), _a(tlen, np.uint32)
+    n = len(qlen)
+    p = params if isinstance(params, Params) else make_params(**params)
+    cfg = JobConfig()
+    dev_arr = None
+    if devices is not None:
+        dev_arr = _a(devices, np.int32)
+        cfg.n_devices = len(dev_arr); cfg.devices = _ptr(dev_arr, i32p)
+    cfg.batch_alns = batch_alns
+    res = {k: np.zeros(n, np.int32) for k in ("score", "query_end", "target_end", "stop", "dstop", "query_start", "target_start")}
+    st = JobStats()
+    check(lib().agatha_align_job_starts(_ptr(qbuf, u8p), _ptr(qoff, u64p), _ptr(qlen, u32p), _ptr(tbuf, u8p), _ptr(toff, u64p), _ptr(tlen, u32p),
+                                        ctypes.c_uint64(n), ctypes.byref(p), ctypes.byref(cfg),
+                                        _ptr(res["score"], i32p), _ptr(res["query_end"], i32p), _ptr(res["target_end"], i32p),
+                                        _ptr(res["stop"], i32p), _ptr(res["dstop"], i32p),
+                                        _ptr(res["query_start"], i32p), _ptr(res["target_start"], i32p), ctypes.byref(st)))
+    out = np.zeros(n, RESULT_DTYPE)
+    for k in RESULT_DTYPE.names:
+        out[k] = res[k]
+    return out, res["query_start"], res["target_start"]
+
+
 def align_pairs(pairs, params, **kw):
     """[(query, target), ...] as str/bytes/uint8 arrays -> structured results (convenience for tests)."""
     qs = [np.frombuffer(q.encode() if isinstance(q, str) else bytes(q), np.uint8) if not isinstance(q, np.ndarray) else q for q, _ in pairs]

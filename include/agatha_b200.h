@@ -102,6 +102,11 @@ int agatha_extend_device(const uint32_t *d_query_packed, const uint32_t *d_targe
                          int32_t *d_score, int32_t *d_query_end, int32_t *d_target_end,
                          int32_t *d_stop, int32_t *d_dstop, void *d_workspace, void *stream);
 
+/* Measured integer issue rates of `device`, in 1e12 lane-operations per second: a stream of VIADDMNMX.U16x2 (the ALU pipe,
+ * which bounds the extension kernels), of IMAD (the FMA pipe), and of both interleaved. A few milliseconds; bench.py calls it
+ * in the same run as the measurement so that the roofline denominator is not a number from another day. Any pointer may be NULL. */
+int agatha_measure_int_peak(int device, double *alu_tera_lane_ops, double *fma_tera_lane_ops, double *mixed_tera_lane_ops);
+
 /* Number of kernel launches issued by this library in the calling process (pack + extend), for bench accounting. */
 uint64_t agatha_launch_count(void);
 
@@ -190,6 +195,17 @@ int agatha_align_job(const uint8_t *query_bases, const uint64_t *query_offsets, 
                      uint64_t n_alns, const agatha_params_t *params, const agatha_job_config_t *cfg,
                      int32_t *score, int32_t *query_end, int32_t *target_end, int32_t *stop, int32_t *dstop,
                      agatha_job_stats_t *stats);
+
+/* The same, plus start positions: gasal_res_t.query_batch_start / target_batch_start (gasal.h:89-90), which the reference
+ * declares but never allocates or fills (res.cpp:27-28; nothing to be bit-compatible with). Convention: GASAL2's WITH_START
+ * (gasal.h:36-39) -- the start of the best-scoring alignment that ends in the reported end cell, found by a second extension
+ * running backwards from that cell over the reversed prefixes (same scoring and band, Z-drop off). A pair whose score is 0
+ * reports the origin. Costs a second pass over the aligned prefixes. Not available together with per-pair ops. */
+int agatha_align_job_starts(const uint8_t *query_bases, const uint64_t *query_offsets, const uint32_t *query_lens,
+                            const uint8_t *target_bases, const uint64_t *target_offsets, const uint32_t *target_lens,
+                            uint64_t n_alns, const agatha_params_t *params, const agatha_job_config_t *cfg,
+                            int32_t *score, int32_t *query_end, int32_t *target_end, int32_t *stop, int32_t *dstop,
+                            int32_t *query_start, int32_t *target_start, agatha_job_stats_t *stats);
 
 /* agatha_align_job keeps its streams (pinned staging, device buffers) for the next call; this frees them. */
 void agatha_release_cached(void);

@@ -216,5 +216,10 @@ int gasal_is_aln_async_done(gasal_gpu_storage_t *gpu_storage);
 /* res.h */
 gasal_res_t *gasal_res_new_host(uint32_t max_n_alns, Parameters *params);
 void gasal_res_destroy_host(gasal_res_t *res);
+gasal_res_t *gasal_res_new_device(gasal_res_t *device_cpy);                         /* res.h:5 */
+gasal_res_t *gasal_res_new_device_cpy(uint32_t max_n_alns, Parameters *params);     /* res.h:6 */
+void gasal_res_destroy_device(gasal_res_t *device_res, gasal_res_t *device_cpy);    /* res.h:9 */
+void gasal_gpu_mem_alloc(gasal_gpu_storage_t *gpu_storage, int gpu_max_query_batch_bytes, int gpu_max_target_batch_bytes, Parameters *params);   /* ctors.h:9 */
+void gasal_gpu_mem_free(gasal_gpu_storage_t *gpu_storage, Parameters *params);      /* ctors.h:11 */
 
 #endif

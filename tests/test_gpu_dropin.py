@@ -16,11 +16,11 @@ DROPIN = os.path.join(os.path.dirname(op.REF_GPU_BIN), "agatha_dropin_manual")
 FLAGS = ["-m", "1", "-x", "4", "-q", "6", "-r", "2", "-s", "3", "-z", "400", "-w", "751"]   # AGAThA.sh:44
 
 
-def _run(binary, qf, tf, workdir, tag, extra=()):
+def _run(binary, qf, tf, workdir, tag, extra=(), flags=None):
     raw = os.path.join(workdir, "raw_%s.log" % tag)
     score = os.path.join(workdir, "score_%s.log" % tag)
     with open(score, "w") as so:
-        r = subprocess.run([binary, "-p"] + FLAGS + list(extra) + [qf, tf, raw], stdout=so, stderr=subprocess.PIPE, text=True, timeout=900)
+        r = subprocess.run([binary, "-p"] + list(flags or FLAGS) + list(extra) + [qf, tf, raw], stdout=so, stderr=subprocess.PIPE, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     return open(score).read(), [float(x) for x in open(raw).read().split()]
 
@@ -99,3 +99,33 @@ def test_reference_driver_with_several_host_threads(tmp_path):
     # 3 threads x ceil(1667/512) batches: one raw.log line per batch (the reference driver appends from its threads without a lock,
     # so a line is occasionally torn in two)
     assert 12 <= len(new_ms) <= 14
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/agatha_ref_manual not built")
+@pytest.mark.parametrize("name,profile,seed,band", [("C3 HiFi-like, wide band", 3, 3, 4095), ("C4 heavy tail, early Z-drop", 4, 4, 751), ("C5 ONT-like", 2, 5, 751)])
+def test_reference_gpu_kernel_agrees_on_2048_pair_slices_of_every_long_workload(tmp_path, name, profile, seed, band):
+    """Full-size pairs of BASELINE configs 3, 4 and 5 against the UNMODIFIED reference GPU program on the same B200:
+    score and both end coordinates of every pair inside the reference's valid domain (lengths < 32768 for
+    its rejoin path, scores <= 32767) must be identical."""
+    import agatha_b200 as ag
+    d = ag.synth_pairs(profile, seed, 2600)
+    ok = np.nonzero((d["qlen"] < 32768) & (d["tlen"] < 32768))[0][:2048]
+    assert len(ok) == 2048
+    sub_q = [d["qbuf"][int(d["qoff"][i]):int(d["qoff"][i]) + int(d["qlen"][i])] for i in ok]
+    sub_t = [d["tbuf"][int(d["toff"][i]):int(d["toff"][i]) + int(d["tlen"][i])] for i in ok]
+    ql = d["qlen"][ok]; tl = d["tlen"][ok]
+    qo = np.concatenate([[0], np.cumsum(ql[:-1], dtype=np.uint64)]).astype(np.uint64)
+    to = np.concatenate([[0], np.cumsum(tl[:-1], dtype=np.uint64)]).astype(np.uint64)
+    qb, tb = np.concatenate(sub_q), np.concatenate(sub_t)
+    qf, tf = str(tmp_path / "q.fasta"), str(tmp_path / "t.fasta")
+    ag.write_fasta(qf, qb, qo, ql)
+    ag.write_fasta(tf, tb, to, tl)
+    flags = FLAGS[:-1] + [str(band)]
+    ref_scores, _ = _run(REF, qf, tf, str(tmp_path), "ref", flags=flags)
+    res, _ = ag.align_job(qb, qo, ql, tb, to, tl, ag.make_params(band_width=band))
+    got = np.array([[r["score"], r["query_end"], r["target_end"]] for r in res])
+    exp = np.array([[int(a), int(b.split("=")[1]), int(c.split("=")[1])] for a, b, c in (ln.split("\t") for ln in ref_scores.splitlines())])
+    inside = got[:, 0] <= 32767                      # the reference's scores wrap beyond int16
+    assert inside.sum() >= 2000, name
+    bad = np.nonzero((got[inside] != exp[inside]).any(axis=1))[0]
+    assert len(bad) == 0, "%s: %d of %d pairs differ, first: ours %s reference %s" % (name, len(bad), inside.sum(), got[inside][bad[0]], exp[inside][bad[0]])

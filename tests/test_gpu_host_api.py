@@ -119,3 +119,40 @@ def test_job_sharded_over_all_visible_gpus(oracle):
     if ndev > 1:
         rev, _ = ag.align_job(d["qbuf"], d["qoff"], d["qlen"], d["tbuf"], d["toff"], d["tlen"], p, devices=list(range(ndev))[::-1])
         assert (rev == one).all()
+
+
+def test_start_positions_reverse_pass_vs_oracle(oracle):
+    """agatha_align_job_starts: GASAL2's WITH_START convention (gasal.h:36-39) -- the reference declares the fields but never
+    fills them (res.cpp:27-28), so this row is pinned by the oracle only: forward extension, then the oracle again on the
+    reversed prefixes that end in the reported cell, Z-drop off."""
+    import agatha_b200 as ag
+    from pairgen import make_pairs
+    pairs = make_pairs(808, 160, 1, 2500, mixed=True) + [("", "ACGT"), ("A", "A"), ("T", "A"), ("ACGTACGT", "ACGTACGT")]
+    # junk in front of a good alignment: the start moves away from the origin
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for _ in range(20):
+        core = acgt[rng.integers(0, 4, int(rng.integers(300, 1500)))]
+        pairs.append((np.concatenate([acgt[rng.integers(0, 4, 40)], core]), np.concatenate([acgt[rng.integers(0, 4, 40)], core])))
+    for pkw in (dict(band_width=751), dict(band_width=127, z_threshold=100), dict(band_width=255, match=2, mismatch=3, gap_open=4, gap_extend=1)):
+        qs = [np.frombuffer(q.encode(), np.uint8) if isinstance(q, str) else q for q, _ in pairs]
+        ts = [np.frombuffer(t.encode(), np.uint8) if isinstance(t, str) else t for _, t in pairs]
+        qlen = np.array([len(x) for x in qs], np.uint32); tlen = np.array([len(x) for x in ts], np.uint32)
+        qoff = np.concatenate([[0], np.cumsum(qlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+        toff = np.concatenate([[0], np.cumsum(tlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+        qbuf = np.concatenate([x for x in qs if len(x)] or [np.zeros(1, np.uint8)]); tbuf = np.concatenate([x for x in ts if len(x)] or [np.zeros(1, np.uint8)])
+        res, qstart, tstart = ag.align_job_starts(qbuf, qoff, qlen, tbuf, toff, tlen, ag.make_params(**pkw))
+        fwd = oracle.align_pairs(list(zip(qs, ts)), op.make_params(**pkw))
+        assert (res["score"] == fwd["score"]).all() and (res["query_end"] == fwd["query_end"]).all() and (res["target_end"] == fwd["target_end"]).all()
+        rev_pairs, live = [], []
+        for i, (q, t) in enumerate(zip(qs, ts)):
+            if len(q) and len(t) and fwd["score"][i] > 0:
+                rev_pairs.append((q[:fwd["query_end"][i] + 1][::-1].copy(), t[:fwd["target_end"][i] + 1][::-1].copy()))
+                live.append(i)
+        kw2 = dict(pkw); kw2["z_threshold"] = -1
+        rev = oracle.align_pairs(rev_pairs, op.make_params(**kw2))
+        exp_q = np.zeros(len(pairs), np.int32); exp_t = np.zeros(len(pairs), np.int32)
+        exp_q[live] = fwd["query_end"][live] - rev["query_end"]; exp_t[live] = fwd["target_end"][live] - rev["target_end"]
+        assert (qstart == exp_q).all() and (tstart == exp_t).all(), (pkw, np.nonzero((qstart != exp_q) | (tstart != exp_t))[0][:5])
+        assert (qstart >= 0).all() and (qstart <= res["query_end"]).all() and (tstart <= res["target_end"]).all()
+        assert (qstart[-20:] > 20).sum() >= 15            # the junk prefixes are trimmed
