@@ -251,34 +251,49 @@ def parse_ref_scores(path):
 # device-resident leg
 # --------------------------------------------------------------------------------------------------------------------
 class DeviceLeg:
-    """One workload, packed on the host and resident in HBM; step() = the extension kernels (packed kernel + redo pass)."""
+    """One workload, packed on the host and resident in HBM; step() = the extension kernels (packed kernel + redo pass) over
+    the whole set. Offsets are 32-bit counts of bases (the reference's batch layout), so a set with more than ~3.5 G bases per
+    side is kept as several chunks and a step launches them back to back."""
 
     def __init__(self, ag, torch, dev, data, params):
         self.ag, self.torch, self.dev = ag, torch, dev
         W = params["band_width"]
         qlen, tlen = data["qlen"], data["tlen"]
         self.n = len(qlen)
-        qw, qoff, _ = ag.pack_batch(data["qbuf"], data["qoff"], qlen, False, n_threads=8)
-        tw, toff, _ = ag.pack_batch(data["tbuf"], data["toff"], tlen, True, n_threads=8)
-        self.packed_bytes = 4 * (len(qw) + len(tw))
-        order = ag.bucket_order(qlen, tlen, W)
-        d32 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
-        pad = np.zeros(64, np.uint32)
-        self.qp = d32(np.concatenate([qw, pad])); self.tp = d32(np.concatenate([tw, pad]))
-        self.meta = [d32(x) for x in (qoff, toff, qlen, tlen, order)]
-        self.p = ag.make_params(**params)
-        self.out = {k: torch.empty(self.n, dtype=torch.int32, device=dev) for k in ("score", "query_end", "target_end", "stop", "dstop")}
-        self.ws = torch.zeros(256, dtype=torch.uint8, device=dev)
         from agatha_b200._lib import check, lib
         self.check, self.L = check, lib()
         self.stream = torch.cuda.current_stream(dev)
+        self.p = ag.make_params(**params)
+        d32 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+        pad = np.zeros(64, np.uint32)
+        big = np.maximum(qlen, tlen).astype(np.int64) + 8
+        bounds, acc, start = [], 0, 0
+        for i in range(self.n):
+            if acc + big[i] > 3_500_000_000:
+                bounds.append((start, i)); start, acc = i, 0
+            acc += big[i]
+        bounds.append((start, self.n))
+        self.chunks = []
+        self.packed_bytes = 0
+        for lo, hi in bounds:
+            ids = np.arange(lo, hi, dtype=np.uint64)
+            qw, qoff, ql = ag.pack_batch(data["qbuf"], data["qoff"], qlen, False, ids=ids, n_threads=8)
+            tw, toff, tl = ag.pack_batch(data["tbuf"], data["toff"], tlen, True, ids=ids, n_threads=8)
+            self.packed_bytes += 4 * (len(qw) + len(tw))
+            order = ag.bucket_order(ql, tl, W)
+            m = hi - lo
+            self.chunks.append({"n": m, "qp": d32(np.concatenate([qw, pad])), "tp": d32(np.concatenate([tw, pad])),
+                                "meta": [d32(x) for x in (qoff, toff, ql, tl, order)],
+                                "out": {k: torch.empty(m, dtype=torch.int32, device=dev) for k in ("score", "query_end", "target_end", "stop", "dstop")},
+                                "ws": torch.zeros(256, dtype=torch.uint8, device=dev)})
 
     def step(self):
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
-        m = self.meta
-        self.check(self.L.agatha_extend_device(vp(self.qp), vp(self.tp), vp(m[0]), vp(m[1]), vp(m[2]), vp(m[3]), vp(m[4]), ctypes.c_uint32(self.n),
-                                               ctypes.byref(self.p), vp(self.out["score"]), vp(self.out["query_end"]), vp(self.out["target_end"]),
-                                               vp(self.out["stop"]), vp(self.out["dstop"]), vp(self.ws), ctypes.c_void_p(self.stream.cuda_stream)))
+        for c in self.chunks:
+            m, o = c["meta"], c["out"]
+            self.check(self.L.agatha_extend_device(vp(c["qp"]), vp(c["tp"]), vp(m[0]), vp(m[1]), vp(m[2]), vp(m[3]), vp(m[4]), ctypes.c_uint32(c["n"]),
+                                                   ctypes.byref(self.p), vp(o["score"]), vp(o["query_end"]), vp(o["target_end"]),
+                                                   vp(o["stop"]), vp(o["dstop"]), vp(c["ws"]), ctypes.c_void_p(self.stream.cuda_stream)))
 
     def timed(self, steps, warmup, barrier=None):
         torch = self.torch
@@ -297,7 +312,7 @@ class DeviceLeg:
         return e0.elapsed_time(e1), [a.elapsed_time(b) for a, b in ev], t0, t1
 
     def results(self):
-        return {k: v.cpu().numpy() for k, v in self.out.items()}
+        return {k: np.concatenate([c["out"][k].cpu().numpy() for c in self.chunks]) for k in ("score", "query_end", "target_end", "stop", "dstop")}
 
 
 def roofline_for(ag, leg, res, kernel_ms, W, int_peak, qlen, tlen, ncu_name=None):
