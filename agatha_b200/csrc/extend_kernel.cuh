@@ -1098,32 +1098,54 @@ struct KernelShape {
     static constexpr int min_blocks = NW == 1 ? (C <= 4 ? 8 : (C <= 24 ? 3 : 2)) : (32 * NW * (C <= 16 ? 128 : (C <= 24 ? 168 : 255)) <= 32768 ? 2 : 1);
 };
 
-// Redo mode (ja.redo != 0): the packed kernel (extend16_kernel.cuh) ran first and marked the pairs it could not finish with
+// Redo mode (template parameter REDO, JobArrays::redo says which instance the host launches): the packed kernel (extend16_kernel.cuh) ran first and marked the pairs it could not finish with
 // REDO_MARK in their query-end slot; this kernel then looks at every pair, 32 candidates per queue access, and aligns the
 // marked ones. A launch without marked pairs costs a few microseconds.
 constexpr int REDO_MARK = INT_MIN;
 
-template <int C, int NW, bool WODD, int JWS>
+template <int C, int NW, bool WODD, int JWS, bool REDO = false>
 __global__ void __launch_bounds__(KernelShape<C, NW>::threads, KernelShape<C, NW>::min_blocks) extend_kernel(JobArrays ja, KernelParams p)
 {
     const int lane = threadIdx.x & 31;
     const int warp = NW == 1 ? 0 : (int)(threadIdx.x >> 5);
     __shared__ GroupShared<(NW > 1 ? NW : 1)> smem;
     GroupShared<NW>* sm = reinterpret_cast<GroupShared<NW>*>(&smem);
-    auto fetch = [&](unsigned step) -> unsigned {       // next queue position, uniform across the group
+    // (REDO is a template parameter, not a run-time mode: the plain kernel keeps exactly the loop it always had)
+    unsigned todo = 0, cand_idx = 0;
+    for (;;) {
+        const unsigned step = (REDO && !todo) ? 32u : 1u;
         unsigned job = 0;
-        if (NW == 1) {
-            if (lane == 0) job = atomicAdd(ja.counter, step);
-            job = __shfl_sync(FULL, job, 0);
+        if (!REDO || !todo) {                          // next queue position, uniform across the group
+            if (NW == 1) {
+                if (lane == 0) job = atomicAdd(ja.counter, step);
+                job = __shfl_sync(FULL, job, 0);
+            } else {
+                __syncthreads();                      // everybody is done with the previous job's shared state
+                if (threadIdx.x == 0) sm->job = atomicAdd(ja.counter, step);
+                __syncthreads();
+                job = sm->job;
+            }
+            if (job >= (unsigned)ja.n) break;
+        } else if (NW > 1) __syncthreads();           // the next alignment re-initialises the group's shared slots
+        unsigned idx;
+        if (!REDO) {
+            idx = ja.order ? __ldg(ja.order + job) : job;
         } else {
-            __syncthreads();                          // everybody is done with the previous job's shared state
-            if (threadIdx.x == 0) sm->job = atomicAdd(ja.counter, step);
-            __syncthreads();
-            job = sm->job;
+            if (!todo) {
+                const unsigned cand = job + (unsigned)lane;
+                bool marked = false;
+                if (cand < (unsigned)ja.n) {
+                    cand_idx = ja.order ? __ldg(ja.order + cand) : cand;
+                    marked = ja.qend[cand_idx] == REDO_MARK;       // written by the previous kernel on this stream: plain load
+                }
+                todo = __ballot_sync(FULL, marked);
+                if (!todo) continue;
+            }
+            const int src = __ffs((int)todo) - 1;
+            todo &= todo - 1u;
+            idx = __shfl_sync(FULL, cand_idx, src);
         }
-        return job;
-    };
-    auto align = [&](unsigned idx) {
+
         Pair pr;
         pr.qlen = (int)__ldg(ja.qlen + idx);
         pr.tlen = (int)__ldg(ja.tlen + idx);
@@ -1145,33 +1167,6 @@ __global__ void __launch_bounds__(KernelShape<C, NW>::threads, KernelShape<C, NW
             if (ja.stop) ja.stop[idx] = stop;
             if (ja.dstop) ja.dstop[idx] = dstop;
         }
-    };
-    // one call site for align() in both modes (a second one would double the kernel's code)
-    unsigned todo = 0, cand_idx = 0;
-    for (;;) {
-        unsigned idx;
-        if (!ja.redo) {
-            const unsigned job = fetch(1u);
-            if (job >= (unsigned)ja.n) break;
-            idx = ja.order ? __ldg(ja.order + job) : job;
-        } else {
-            if (!todo) {
-                const unsigned first = fetch(32u);
-                if (first >= (unsigned)ja.n) break;
-                const unsigned cand = first + (unsigned)lane;
-                bool marked = false;
-                if (cand < (unsigned)ja.n) {
-                    cand_idx = ja.order ? __ldg(ja.order + cand) : cand;
-                    marked = ja.qend[cand_idx] == REDO_MARK;       // written by the previous kernel on this stream: plain load
-                }
-                todo = __ballot_sync(FULL, marked);
-                if (!todo) continue;
-            } else if (NW > 1) __syncthreads();               // the next alignment re-initialises the group's shared slots
-            const int src = __ffs((int)todo) - 1;
-            todo &= todo - 1u;
-            idx = __shfl_sync(FULL, cand_idx, src);
-        }
-        align(idx);
     }
 }
 

@@ -41,10 +41,18 @@ int launch_variant(const JobArrays& ja, const KernelParams& kp, cudaStream_t st)
     // persistent groups: never more groups than jobs, otherwise fill every SM
     const int groups_per_block = NW == 1 ? 4 : 1;
     long long want = ((long long)ja.n + groups_per_block - 1) / groups_per_block;
-    long long grid = persistent_grid(extend_kernel<C, NW, WODD, JWS>, threads);
+    // the redo pass exists for the variants the packed kernel precedes: W = 7 (mod 8), at least 8 cells per lane
+    constexpr bool HAS_REDO = WODD && JWS >= 0 && C >= 8;
+    if (ja.redo && !HAS_REDO) return set_error(AGATHA_EUNSUPPORTED, "no redo pass for this kernel variant");
+    long long grid = persistent_grid(extend_kernel<C, NW, WODD, JWS, false>, threads);
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    extend_kernel<C, NW, WODD, JWS><<<(unsigned)grid, threads, 0, st>>>(ja, kp);
+    if constexpr (HAS_REDO) {
+        if (ja.redo) extend_kernel<C, NW, WODD, JWS, true><<<(unsigned)grid, threads, 0, st>>>(ja, kp);
+        else extend_kernel<C, NW, WODD, JWS, false><<<(unsigned)grid, threads, 0, st>>>(ja, kp);
+    } else {
+        extend_kernel<C, NW, WODD, JWS, false><<<(unsigned)grid, threads, 0, st>>>(ja, kp);
+    }
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_error(e, "extend_kernel launch");

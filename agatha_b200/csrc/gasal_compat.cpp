@@ -2,6 +2,7 @@
 // Written from the interface description in SURVEY.md section 8(b) and the declarations in the reference headers;
 // behaviour notes cite the reference implementation they reproduce.
 #include <algorithm>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -260,7 +261,14 @@ void gasal_aln_async(gasal_gpu_storage_t* g, const uint32_t actual_query_batch_b
         if (agatha_stream_wait(s)) die("gasal_aln_async");
         float ms[3];
         agatha_stream_timings(s, ms);
-        params->raw_file << ms[1] << std::endl;
+        // one whole line per batch even when several driver threads (-n) share the stream object (the reference writes from
+        // its threads without a lock, gasal_align.cu:233, and tears lines now and then)
+        static std::mutex raw_mu;
+        std::lock_guard<std::mutex> lk(raw_mu);
+        char line[64];
+        const int len = snprintf(line, sizeof(line), "%g\n", (double)ms[1]);
+        params->raw_file.write(line, len);
+        params->raw_file.flush();
     }
     g->is_free = 0;
 }

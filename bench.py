@@ -43,7 +43,7 @@ WORKLOADS = {   # name: (profile, seed, pairs, band, description)
     "C4": (4, 4, 100000, 751, "C4: heavy-tailed lengths (1-100 kb), 10 % error, half of the reads turn random (early Z-drop), -w 751"),
     "C5": (2, 5, 1000000, 751, "C5: 1M synthetic ONT-like pairs sharded over the GPUs (strong scaling), " + SCORING + " -w 751"),
 }
-EXTRA_LEGS = {"C1": 8192, "C3": 4096, "C4": 32768}     # kernel-only legs at N = 1 (pairs per leg: a few seconds in total)
+EXTRA_LEGS = {"C1": 8192, "C3": 8192, "C4": 100000}    # kernel-only legs at N = 1 (pairs per leg: a few seconds in total)
 
 
 def load_hbm_peak():

@@ -78,7 +78,10 @@ int agatha_pack_device(const uint8_t *d_query_bases, uint64_t query_bytes,
  * code). Replaces gasal_reversecomplement_kernel (kernels/pack_rc_seqs.h:56-212), which gasal_aln_async launches after
  * packing when params->isReverseComplement is set (gasal_align.cu:199-212). Call it AFTER agatha_pack_device on the same
  * stream, with the same ASCII batch: sequences whose op is non-zero are packed again with the operation applied to their
- * real bases (the 'N' padding stays behind the sequence); sequences with op 0 are left alone. */
+ * real bases (the 'N' padding stays behind the sequence); sequences with op 0 are left alone.
+ * NOTE: bit 0 implements the INTENDED reverse. The reference's kernel, as compiled, does not reverse anything useful
+ * (its padding counter compares 4-bit codes with N_CODE = 0x4E and is always 0), so results on
+ * reversed sequences are pinned by this repository's oracle, not by the reference GPU binary. The complement bit is identical. */
 int agatha_apply_ops_device(const uint8_t *d_query_bases, const uint8_t *d_target_bases,
                             const uint32_t *d_query_offsets, const uint32_t *d_target_offsets,
                             const uint32_t *d_query_lens, const uint32_t *d_target_lens,

@@ -133,10 +133,15 @@ struct EmuLauncher {
     template <int C, int NW, bool WODD, int JWS> int run() const
     {
         struct Ctx { const JobArrays* ja; const KernelParams* kp; } ctx{&ja, &kp};
-        emu::run_block(KernelShape<C, NW>::threads, [](void* a) {
-            Ctx* c = (Ctx*)a;
-            extend_kernel<C, NW, WODD, JWS>(*c->ja, *c->kp);
-        }, &ctx);
+        constexpr bool HAS_REDO = WODD && JWS >= 0 && C >= 8;           // as in extend_launch.cuh
+        if (ja.redo && !HAS_REDO) return set_error(AGATHA_EUNSUPPORTED, "no redo pass for this kernel variant");
+        if constexpr (HAS_REDO) {
+            if (ja.redo) {
+                emu::run_block(KernelShape<C, NW>::threads, [](void* a) { Ctx* c = (Ctx*)a; extend_kernel<C, NW, WODD, JWS, true>(*c->ja, *c->kp); }, &ctx);
+                return AGATHA_OK;
+            }
+        }
+        emu::run_block(KernelShape<C, NW>::threads, [](void* a) { Ctx* c = (Ctx*)a; extend_kernel<C, NW, WODD, JWS, false>(*c->ja, *c->kp); }, &ctx);
         return AGATHA_OK;
     }
     template <int C, int NW, int JWS> int run16() const

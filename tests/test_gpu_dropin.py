@@ -96,9 +96,7 @@ def test_reference_driver_with_several_host_threads(tmp_path):
     ref_scores, _ = _run(REF, qf, tf, str(tmp_path), "ref1", extra=("-a", "512"))
     new_scores, new_ms = _run(DROPIN, qf, tf, str(tmp_path), "new3", extra=("-n", "3", "-a", "512"))
     assert sorted(new_scores.splitlines()) == sorted(ref_scores.splitlines())
-    # 3 threads x ceil(1667/512) batches: one raw.log line per batch (the reference driver appends from its threads without a lock,
-    # so a line is occasionally torn in two)
-    assert 12 <= len(new_ms) <= 14
+    assert len(new_ms) == 12          # 3 threads x ceil(1667/512) batches: one whole raw.log line per batch (the shim locks the file)
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/agatha_ref_manual not built")

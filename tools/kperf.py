@@ -30,13 +30,14 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true", help="compare a 48-pair sample with the oracle")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per workload (overrides the slice sizes)")
     args = ap.parse_args()
     import torch
     import agatha_b200 as ag
     dev = torch.device("cuda:0")
     for name in args.configs.split(","):
         prof, seed, n, W = CONFIGS[name]
-        n = max(64, int(n * args.scale))
+        n = args.pairs or max(64, int(n * args.scale))
         dd = ag.synth_pairs(prof, seed, n)
         stq, qoff, qlen = ag.stage_batch(dd["qbuf"], dd["qoff"], dd["qlen"])
         stt, toff, tlen = ag.stage_batch(dd["tbuf"], dd["toff"], dd["tlen"])

@@ -6,7 +6,7 @@ import json
 import sys
 
 
-def main(path):
+def main(path, extra=()):
     rows = list(csv.reader(open(path)))
     hdr = rows[0]
     units = rows[1]
@@ -36,8 +36,8 @@ def main(path):
         "thread_insts": f("smsp__thread_inst_executed.sum"),
         "warps_active_pct": f("sm__warps_active.avg.pct_of_peak_sustained_active"),
         "icache_hit_pct": f("sm__icc_requests_lookup_hit.sum") and f("sm__icc_requests.sum") and 100.0 * f("sm__icc_requests_lookup_hit.sum") / f("sm__icc_requests.sum"),
-        "dram_bytes": (f("dram__bytes_read.sum") or 0) + (f("dram__bytes_write.sum") or 0),
-        "dram_unit": u.get("dram__bytes_read.sum"),
+        "dram_bytes_per_launch": sum((f(k) or 0) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u.get(k), 1)
+                                     for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")),
         "local_ld": f("smsp__inst_executed_op_local_ld.sum"), "local_st": f("smsp__inst_executed_op_local_st.sum"),
         "shared_ld": f("smsp__inst_executed_op_shared_ld.sum"), "shared_st": f("smsp__inst_executed_op_shared_st.sum"),
     }
@@ -48,8 +48,12 @@ def main(path):
             if v is not None:
                 stalls[k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]] = round(v, 3)
     out["stalls_per_issue"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:8])
+    out = {k: v for k, v in out.items() if v is not None}
+    for a in extra:
+        k, _, v = a.partition("=")
+        out[k] = int(v) if v.isdigit() else v
     print(json.dumps(out, indent=1))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2:])
