@@ -418,7 +418,6 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     int ev_lane_h = 0, ev_h = 0;
     bool ev_empty = false;
     unsigned vm2 = 0u;                                                   // tail: valid-cell bits of the anti-diagonal being computed
-    auto half_mask = [&](int jj) -> unsigned { return (unsigned)imad((int)((vm2 >> jj) & 0x00010001u), p.m16, 0); };
     auto owner_warp = [&](int h, int par) -> int {                      // highest warp whose maximum is h (ties -> largest target index)
         if (NW == 1) return 0;
         const unsigned who = __ballot_sync(FULL, lane < NW && sm->scan_h[par][lane < NW ? lane : 0] == h);
@@ -453,7 +452,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         ev_lane_h = lane_h; ev_h = h;
         return true;
     };
-    auto scan_slow = [&](const unsigned (&A)[P], int dd, int u, bool tailm) -> bool {   // tailm: constant at every call site
+    // mask: 0 none, 1 the tail's valid-cell bits (vm2), 2 prologue -- the cells beyond the near matrix edges (|k| > dd) hold
+    // matrix-edge values injected after the step, which are not cells of this anti-diagonal (constant at every call site)
+    auto scan_slow = [&](const unsigned (&A)[P], int dd, int u, int mask) -> bool {
         resolve();                                                       // the test needs (mt, mq) ...
         sync_state();                                                    // ... and the maximum as a true score
         if (ev_empty) { ev_empty = false; return scan_update(st, INT_MIN, 0, dd, u, p); }   // no cell on this anti-diagonal
@@ -462,9 +463,16 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         if (NW == 1 || warp == ow) {
             const unsigned who = __ballot_sync(FULL, ev_lane_h == ev_h);
             const int src = 31 - __clz((int)who);
+            unsigned m2 = vm2;
+            if (mask == 2) {
+                const int k0 = -W + 2 * C * gl + u;
+                const int a_ = max((-dd - k0 + 1) >> 1, 0), b_ = min((dd - k0) >> 1, C - 1);
+                const unsigned fm = (b_ >= a_) ? ((0xffffffffu >> (31 - b_)) & (0xffffffffu << a_)) : 0u;
+                m2 = (fm & ((1u << P) - 1u)) | ((fm >> P) << 16);
+            }
             unsigned B[P];
 #pragma unroll
-            for (int jj = 0; jj < P; jj++) B[jj] = tailm ? (A[jj] & half_mask(jj)) : A[jj];
+            for (int jj = 0; jj < P; jj++) B[jj] = mask ? (A[jj] & (unsigned)imad((int)((m2 >> jj) & 0x00010001u), p.m16, 0)) : A[jj];
             const int jb = __shfl_sync(FULL, search(B, ev_h), src);
             g = C * (32 * warp + src) + jb;
         }
@@ -492,7 +500,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     // MODE 0 steady state (every in-band cell inside the matrix); 1 prologue (d <= W: what lies beyond the matrix edges is
     // dead, the caller injects the edge cells after the scan); 2 tail (far edges: cells outside the matrix are masked out of
     // the maximum, padding columns are patched). BLK: inside a steady-state block (feeds prepared by the caller).
-    auto step16 = [&](int dd, bool scan, auto u_tag, auto mode_tag, auto blk_tag) -> bool {
+    auto step16 = [&](int dd, bool scan, auto u_tag, auto mode_tag, auto blk_tag, auto& inject) -> bool {
         constexpr int U = decltype(u_tag)::value;
         constexpr int MODE = decltype(mode_tag)::value;
         constexpr bool PRO = MODE == 1, TAILM = MODE == 2, BLK = decltype(blk_tag)::value != 0;
@@ -526,6 +534,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             AE[JP] = prmt(AE[JP], floor2, edge_sel);                    // band-edge lane: nothing leaks into k = W+1
             if (BLK) shift_ref_blk(); else shift_ref();
             if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }   // inputs of the next anti-diagonal
+            // prologue: the matrix-edge cells of this anti-diagonal, BEFORE the hand-over slot is published (an injected E / F
+            // at the first or last cell of a warp is read by the neighbouring warp)
+            if (PRO) { if (dd < W) inject(dd, u_tag); }
             if (NW > 1) { if (lane == 0) sm->edgeF[warp] = AF[0]; }
         } else {
             unsigned y = __shfl_down_sync(FULL, AF[0], 1);               // neighbour's (F[0], F[P])
@@ -539,6 +550,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             if (!PRO) AF[JP] = prmt(AF[JP], floor2, edge_sel);
             if (BLK) shift_query_blk(); else shift_query();
             if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }
+            if (PRO) { if (dd < W) inject(dd, u_tag); }
             if (NW > 1) { if (lane == 31) sm->edgeE[warp] = AE[P - 1]; }
         }
         if (!scan) {                                                     // computed, not scanned (d >= L before the wrap-up)
@@ -612,34 +624,29 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     // The prologue, d = 0 .. W. Inside it no value can leave the 16-bit range (host-side bound, extend_dispatch.h), so there
     // is no range check. The scan -- including the search for the position of a low maximum -- runs BEFORE the injection, so
     // an injected edge value can never be mistaken for the anti-diagonal's maximum.
+    auto inject_pro = [&](int dd, auto u_tag) { inject16_sw(dd, u_tag, (dd >> 1) & 3); };
     for (;;) {
         int ev = 0;
 #pragma unroll 1
         for (; d < W; d += 2) {
-            const int S = (d >> 1) & 3;
-            if (S == 0) {                                                // a new block of 8
+            if ((d & 7) == 0) {                                          // a new block of 8
                 blk_qt = ((d + W + 1) >> 3) - NG * gl;
                 blk_ql = ((W + 1 - d) >> 3) - 1 - NG * gl;
                 blk_last = (d + 7 == W);
                 block_selectors();
             }
-            if (step16(d, true, U1{}, MPRO{}, NOBLK{})) { ev = 1; break; }
-            inject16_sw(d, U1{}, S);                                     // d <= W - 1: always an injection
-            if (step16(d + 1, true, U0{}, MPRO{}, NOBLK{})) { ev = 2; break; }
-            if (d + 1 < W) inject16_sw(d + 1, U0{}, S);                  // nothing after the anti-diagonal d == W
+            if (step16(d, true, U1{}, MPRO{}, NOBLK{}, inject_pro)) { ev = 1; break; }
+            if (step16(d + 1, true, U0{}, MPRO{}, NOBLK{}, inject_pro)) { ev = 2; break; }
         }
         if (!ev) break;
         // cold: a closer look at the anti-diagonal that might fire, then finish the pair of steps
-        const int S = (d >> 1) & 3;
         if (ev == 1) {
-            if (scan_slow(A1, d, 1, false)) { fired = true; break; }
-            inject16_sw(d, U1{}, S);
-            if (step16(d + 1, true, U0{}, MPRO{}, NOBLK{})) ev = 2;
+            if (scan_slow(A1, d, 1, 2)) { fired = true; break; }
+            if (step16(d + 1, true, U0{}, MPRO{}, NOBLK{}, inject_pro)) ev = 2;
         }
         if (ev == 2) {
-            if (scan_slow(A0, d + 1, 0, false)) { fired = true; d++; break; }
+            if (scan_slow(A0, d + 1, 0, 2)) { fired = true; d++; break; }
         }
-        if (d + 1 < W) inject16_sw(d + 1, U0{}, S);
         d += 2;
     }
 
@@ -662,24 +669,24 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
 #if AGATHA_INLINE_EVENTS
 #pragma unroll 1
             for (; d < dblk; d += 2) {
-                if (step16(d, true, U1{}, MSTEADY{}, INBLK{})) { if (scan_slow(A1, d, 1, false)) { fired = true; break; } }
-                if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{})) { if (scan_slow(A0, d + 1, 0, false)) { fired = true; d++; break; } }
+                if (step16(d, true, U1{}, MSTEADY{}, INBLK{}, inject_pro)) { if (scan_slow(A1, d, 1, 0)) { fired = true; break; } }
+                if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{}, inject_pro)) { if (scan_slow(A0, d + 1, 0, 0)) { fired = true; d++; break; } }
             }
 #else
             while (d < dblk) {
                 int ev = 0;
 #pragma unroll 1
                 for (; d < dblk; d += 2) {
-                    if (step16(d, true, U1{}, MSTEADY{}, INBLK{})) { ev = 1; break; }
-                    if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{})) { ev = 2; break; }
+                    if (step16(d, true, U1{}, MSTEADY{}, INBLK{}, inject_pro)) { ev = 1; break; }
+                    if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{}, inject_pro)) { ev = 2; break; }
                 }
                 if (!ev) break;
                 if (ev == 1) {
-                    if (scan_slow(A1, d, 1, false)) { fired = true; break; }
-                    if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{})) ev = 2;   // finish the pair (cold copy of the second step)
+                    if (scan_slow(A1, d, 1, 0)) { fired = true; break; }
+                    if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{}, inject_pro)) ev = 2;   // finish the pair (cold copy of the second step)
                 }
                 if (ev == 2) {
-                    if (scan_slow(A0, d + 1, 0, false)) { fired = true; d++; break; }
+                    if (scan_slow(A0, d + 1, 0, 0)) { fired = true; d++; break; }
                 }
                 d += 2;
             }
@@ -716,16 +723,16 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
                     if (ss > se) { ev = 3; break; }
                     next_slice += span;
                 }
-                if (step16(d, d < pr.L || d >= wrap_lo, U1{}, MTAIL{}, NOBLK{})) { ev = 1; break; }
-                if (d + 1 < d_end) { if (step16(d + 1, d + 1 < pr.L || d + 1 >= wrap_lo, U0{}, MTAIL{}, NOBLK{})) { ev = 2; break; } }
+                if (step16(d, d < pr.L || d >= wrap_lo, U1{}, MTAIL{}, NOBLK{}, inject_pro)) { ev = 1; break; }
+                if (d + 1 < d_end) { if (step16(d + 1, d + 1 < pr.L || d + 1 >= wrap_lo, U0{}, MTAIL{}, NOBLK{}, inject_pro)) { ev = 2; break; } }
             }
             if (ev == 3) { stop = AGATHA_STOP_BANDEXIT; d_stop = min(next_slice, pr.L); band_exit = true; break; }
             if (ev == 1) {
-                if (scan_slow(A1, d, 1, true)) { fired = true; break; }
-                if (d + 1 < d_end) { if (step16(d + 1, d + 1 < pr.L || d + 1 >= wrap_lo, U0{}, MTAIL{}, NOBLK{})) ev = 2; }
+                if (scan_slow(A1, d, 1, 1)) { fired = true; break; }
+                if (d + 1 < d_end) { if (step16(d + 1, d + 1 < pr.L || d + 1 >= wrap_lo, U0{}, MTAIL{}, NOBLK{}, inject_pro)) ev = 2; }
             }
             if (ev == 2) {
-                if (scan_slow(A0, d + 1, 0, true)) { fired = true; d++; break; }
+                if (scan_slow(A0, d + 1, 0, 1)) { fired = true; d++; break; }
             }
             if (ev) d += 2;
         }
