@@ -1,4 +1,6 @@
-// Banded affine-gap extension with Z-drop for sm_100a: the hot path of this repository.
+// Banded affine-gap extension with Z-drop for sm_100a: the GENERAL kernel -- every band width, every symbol, int32 state.
+// The hot path of the shipped workloads is the packed kernel in extend16_kernel.cuh; this kernel aligns the pairs that one
+// marks (redo pass) and everything the packed kernel does not take (W not 7 mod 8, W < 135, scoring outside its table, ...).
 //
 // Replaces the reference's agatha_kernel (AGAThA/src/kernels/agatha_kernel.h:49-431) + agatha_sort (:434-458);
 // same results (score, query end, target end), different algorithm layout. Parity spec: SURVEY.md Appendix A,
@@ -13,8 +15,10 @@
 // (one warp shuffle per step). The per-anti-diagonal maximum needed by the Z-drop test is a lane-local max of
 // (H*32+j) keys, one warp REDUX per step and a warp-uniform scalar update: the scan is exact per anti-diagonal,
 // so a terminated alignment stops at once and the warp pulls the next job (work redistribution on termination).
-// Per cell, ALU pipe: IDP.4A (score byte select + add), VIMNMX3 (H), 2x VIADDMNMX (E, F), 1/2 VIMNMX3 (tracking);
-// FMA pipe: IMAD for t = M - goe and for the tracking key. ncu on the bench launch: ALU pipe 78.7 % busy.
+// Per cell of the 32-bit loops, ALU pipe: IDP.4A (score byte select + add), VIMNMX3 (H), 2x VIADDMNMX (E, F), 1/2 VIMNMX3
+// (tracking); FMA pipe: IMAD for t = M - goe and for the tracking key. One-warp shapes with W = 7 (mod 8) may run their
+// prologue and steady state on 16-bit packed state (run_fast16, AGATHA_S16=1/2) -- round 1's fast path, superseded by
+// extend16_kernel.cuh and kept for A/B measurements.
 #pragma once
 
 #include <cstdint>

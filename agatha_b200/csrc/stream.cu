@@ -69,7 +69,9 @@ agatha_stream_t* agatha_stream_create(int device, uint32_t max_alns, uint64_t ma
     auto* s = new agatha_stream();
     s->device = device;
     if ((e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking)) != cudaSuccess) { cuda_error(e, "cudaStreamCreate"); delete s; return nullptr; }
-    for (auto& ev : s->ev) cudaEventCreate(&ev);
+    // blocking waits: a host thread that waits for a batch sleeps instead of spinning -- with one process per GPU and the
+    // packing threads of 8 ranks on 32 cores, spinning waiters take cores away from the packers
+    for (auto& ev : s->ev) cudaEventCreateWithFlags(&ev, cudaEventBlockingSync);
     if ((e = cudaMalloc(&s->d_ws, AGATHA_WORKSPACE_BYTES)) != cudaSuccess) { cuda_error(e, "cudaMalloc(workspace)"); agatha_stream_destroy(s); return nullptr; }
     if (agatha_stream_reserve(s, std::max<uint32_t>(max_alns, 1), std::max<uint64_t>(max_query_bytes, 8), std::max<uint64_t>(max_target_bytes, 8)) != AGATHA_OK) {
         agatha_stream_destroy(s);

@@ -368,6 +368,21 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, rank)
 
+    # One rank per GPU on one box: give every rank its own slice of the host cores (and, by first touch, host memory on the
+    # socket those cores belong to). Without it the ranks' packing threads and pinned staging land on arbitrary sockets and the
+    # end-to-end legs of 8 ranks share the cross-socket link.
+    pinned_cores = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            lw = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            per = max(1, len(cores) // lw)
+            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            pinned_cores = [mine[0], mine[-1]]
+        except OSError:
+            pass
+
     import agatha_b200 as ag
     from agatha_b200._lib import DEFAULT_PARAMS
     import torch
@@ -524,6 +539,7 @@ def main():
             "config": {"workload": desc, "pairs_total": total, "pairs_this_rank": n,
                        "l2": "packed inputs (%.2f GB per GPU) exceed the 126 MB L2" % (leg_bytes(data) / 1e9),
                        "parallelism": "independent pairs, %d GPU(s), rank r aligns pairs [r*T/N, (r+1)*T/N) of the fixed set, no collective on the data path" % world,
+                       "host_cores_rank0": pinned_cores, "host_packing_threads_per_rank": stg,
                        "scaling_note": "N = 1 is C2 (100k pairs); N > 1 shard the fixed 1M-pair C5 set of the same generator: value(N) / (N x value(1)) is the strong-scaling efficiency",
                        "stops_rank0": {"end": int((stops == 0).sum()), "zdrop": int((stops == 1).sum()), "bandexit": int((stops == 2).sum())}},
             "gcups": float(cells_t.item()) / (ms_step * 1e-3) / 1e9,
