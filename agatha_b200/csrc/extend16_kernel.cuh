@@ -57,6 +57,36 @@ struct Shape16 {
     static constexpr int min_blocks = NW == 1 ? (C <= 24 ? AGATHA_MB24 : 3) : (NW == 2 ? 6 : (NW == 4 ? AGATHA_MBW4 : 1));
 };
 
+// Shared-memory barrier with split arrive / wait (mbarrier): one elected lane per warp arrives, every lane waits on the phase
+// parity. Used by the pipelined steady state of multi-warp groups, where a warp signals "my edge value of this anti-diagonal
+// is published" long before it needs its neighbours' (a __syncthreads would make it wait right there).
+#ifdef AGATHA_HOST_EMU
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) { emu::mbar_init(b, count); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { emu::mbar_arrive(b); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) { emu::mbar_wait(b, parity); }
+#else
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b)                 // release: orders this thread's earlier shared-memory writes
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity)  // acquire: returns once the phase of that parity is complete
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "AGATHA_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra AGATHA_MBAR_DONE;\n"
+        "bra AGATHA_MBAR_WAIT;\n"
+        "AGATHA_MBAR_DONE:\n"
+        "}" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+}
+#endif
+
 // Scoring and recurrence constants of one alignment, held in plain registers: ptxas otherwise re-materialises them from the
 // constant bank inside the hot loop (12 moves per two anti-diagonals for the PRMT table alone).
 struct Consts16 {
@@ -118,6 +148,26 @@ __device__ __forceinline__ unsigned cells16(unsigned (&H)[C / 2], unsigned (&E)[
     return best;
 }
 
+// The edge value a step of parity U hands to the neighbouring lane, computed on its own: (F[0], F[P]) for U == 0, (E[P-1],
+// E[C-1]) for U == 1. It depends on this lane's state only -- not on the edge value coming in during the same step -- which is
+// what lets a warp of a multi-warp group publish it before it waits for its neighbours (pipelined steady state). Same
+// operations on the same inputs as the corresponding register in cells16.
+template <int C, int U>
+__device__ __forceinline__ unsigned out_edge16(const unsigned (&H)[C / 2], const unsigned (&E)[C / 2], const unsigned (&F)[C / 2],
+                                               const uint32_t (&Qw)[C / 8], const uint32_t (&Rw)[C / 8], const Consts16& k)
+{
+    constexpr int P = C / 2;
+    constexpr int jj = (U == 0) ? 0 : P - 1, a = jj, b = jj + P;
+    const unsigned xa = Qw[a >> 3] ^ Rw[a >> 3], xb = Qw[b >> 3] ^ Rw[b >> 3];
+    const unsigned sa = prmt(k.tab_lo, k.tab_hi, ((a >> 2) & 1) ? (xa >> 16) : xa);
+    const unsigned sb = prmt(k.tab_lo, k.tab_hi, ((b >> 2) & 1) ? (xb >> 16) : xb);
+    const unsigned sel = (unsigned)(a & 3) | ((unsigned)((a & 3) | 8) << 4) | ((unsigned)(4 + (b & 3)) << 8) | ((unsigned)((4 + (b & 3)) | 8) << 12);
+    const unsigned s2 = prmt(sa, sb, sel);
+    const unsigned m = (unsigned)imad((int)H[jj], k.one, (int)s2);
+    const unsigned t = (unsigned)imad((int)m, k.one, k.ct[U]);
+    return __viaddmax_u16x2(U == 0 ? F[0] : E[P - 1], k.ce[U], t);
+}
+
 // Symbols the packed kernel scores: query {A,C,G,T}, target {A,C,G,T,N} (codes 0..3 and TCODE_N, which the windows hold as
 // TCODE_N & 7 = 5 so that every code XOR stays below 8 and indexes the table directly). Anything else -- including an N in
 // the read -- goes to the general kernel.
@@ -143,17 +193,24 @@ __device__ __forceinline__ bool outside_packed_alphabet(const Pair& pr, int lane
 template <int C, int NW>
 struct Shared16 {
     unsigned snap[Shape16<C, NW>::warps][C / 2][32];   // snapshot of the anti-diagonal holding the running maximum: [warp][register][lane]
-    unsigned edgeE[NW];       // (E[P-1], E[C-1]) of lane 31 of each warp, published after steps of parity 1
-    unsigned edgeF[NW];       // (F[0], F[P]) of lane 0 of each warp, published after steps of parity 0
-    int scan_h[2][NW];        // per-warp maximum of the anti-diagonal (stored domain), slots alternate by anti-diagonal parity
+    // hand-over between the warps of a group: the step of anti-diagonal d writes slot (d >> 1) & 1, the step of d + 1 reads it
+    // (two slots: in the pipelined steady state a warp publishes the value of d + 2 while a neighbour may still read that of d)
+    unsigned edgeE[2][NW];    // (E[P-1], E[C-1]) of lane 31 of each warp, published by steps of parity 1 (even d)
+    unsigned edgeF[2][NW];    // (F[0], F[P]) of lane 0 of each warp, published by steps of parity 0 (odd d)
+    unsigned evsnap[NW > 1 ? Shape16<C, NW>::warps : 1][NW > 1 ? C / 2 : 1][32];   // pipelined steady state: H of an anti-diagonal that may fire Z-drop
+    int scan_h[4][NW];        // per-warp maximum of the anti-diagonal (stored domain), ring of four slots indexed by d & 3
     int rng[2][NW];           // per-warp live minimum / maximum for the range monitor
     int bcast;                // cell index found by the owner warp
     unsigned job;
+    // NW > 1: arrive / wait barriers of the pipelined steady state, one arrival per warp and anti-diagonal; anti-diagonal d uses
+    // barrier d & 1 (a warp arrives for d before it waits for d-1, and a barrier counts arrivals, not warps: on a single barrier
+    // the early arrival would be taken for the phase that is still open)
+    alignas(8) uint64_t mbar[2];
 };
 
 // One alignment on packed state. Returns false when the pair has to be redone by the general kernel (nothing written).
 template <int C, int NW, int JWS>
-__device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p, int lane, int warp, int cta_warp, Shared16<C, NW>* sm,
+__device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p, int lane, int warp, int cta_warp, Shared16<C, NW>* sm, unsigned& mphase,
                                            int& out_score, int& out_qend, int& out_tend, int& out_stop, int& out_dstop)
 {
     static_assert(C % 8 == 0 && C <= 32 && JWS >= 0 && JWS < C && (JWS & 7) == 7, "packed kernel: C multiple of 8, W = 7 (mod 8)");
@@ -304,7 +361,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     const int neg_ok = NEG16 + p.goe + p.ge + 17 * X + 64;
 
     // ---- snapshot of the anti-diagonal that holds the running maximum (shared memory) ------------------------------------
-    int snap_d = -1, snap_u = 0, snap_src = 0, snap_w = 0, snap_h = 0;
+    int snap_d = -1, snap_u = 0, snap_w = 0, snap_h = 0;
     // (scalar stores: a vector store would need the state registers in aligned quadruples, which costs moves in the hot path)
     auto snapshot = [&](const unsigned (&A)[P], unsigned keep_bits, bool masked) {
 #pragma unroll
@@ -313,6 +370,10 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             if (masked) x &= (unsigned)imad((int)((keep_bits >> jj) & 0x00010001u), p.m16, 0);   // cells outside the matrix never match
             sm->snap[cta_warp][jj][lane] = x;
         }
+    };
+    auto snapshot_ev = [&](const unsigned (&A)[P]) {                    // NW > 1, cold: an anti-diagonal that may fire, for pipe_drain
+#pragma unroll
+        for (int jj = 0; jj < (NW > 1 ? P : 0); jj++) sm->evsnap[cta_warp][jj][lane] = A[jj];
     };
     auto search = [&](const unsigned (&A)[P], int h) -> int {          // largest cell index whose stored value is h, -1 if none
         int jl = -1, jh = -1;
@@ -336,8 +397,10 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             unsigned S[P];
 #pragma unroll
             for (int jj = 0; jj < P; jj++) S[jj] = sm->snap[cta_warp][jj][lane];
-            const int jb = __shfl_sync(FULL, search(S, snap_h), snap_src);
-            g = C * (32 * warp + snap_src) + jb;
+            // ties go to the largest target index: the highest lane that holds the value, its highest cell
+            const int jb = search(S, snap_h);
+            const int src = 31 - __clz((int)__ballot_sync(FULL, jb >= 0));
+            g = C * (32 * warp + src) + __shfl_sync(FULL, jb, src);
         }
         g = group_bcast(g, snap_w);
         const int k = -W + 2 * g + snap_u;
@@ -405,8 +468,8 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         }
         if (NW > 1) {
             // the hand-over slots hold values of the old base (and possibly dead cells that were just reset): publish again
-            if (lane == 31) sm->edgeE[warp] = AE[P - 1];
-            if (lane == 0) sm->edgeF[warp] = AF[0];
+            if (lane == 31) { sm->edgeE[0][warp] = AE[P - 1]; sm->edgeE[1][warp] = AE[P - 1]; }
+            if (lane == 0) { sm->edgeF[0][warp] = AF[0]; sm->edgeF[1][warp] = AF[0]; }
             __syncthreads();
         }
         return true;
@@ -415,41 +478,36 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     // ---- Termination Condition & Score Update (agatha_kernel.h:292-314) on a packed anti-diagonal -------------------------
     // scan_fast runs in the hot loops: nothing to do, or a new maximum (snapshot for the lazy argmax); returns true when the
     // anti-diagonal might fire Z-drop -> scan_slow, outside the hot loops.
-    int ev_lane_h = 0, ev_h = 0;
+    int ev_h = 0;
     bool ev_empty = false;
     unsigned vm2 = 0u;                                                   // tail: valid-cell bits of the anti-diagonal being computed
-    auto owner_warp = [&](int h, int par) -> int {                      // highest warp whose maximum is h (ties -> largest target index)
+    auto owner_warp = [&](int h, int slot) -> int {                     // highest warp whose maximum is h (ties -> largest target index)
         if (NW == 1) return 0;
-        const unsigned who = __ballot_sync(FULL, lane < NW && sm->scan_h[par][lane < NW ? lane : 0] == h);
+        const unsigned who = __ballot_sync(FULL, lane < NW && sm->scan_h[slot][lane < NW ? lane : 0] == h);
         return 31 - __clz((int)who);
     };
     // The maximum over the warp of both halves of best2 without touching the ALU pipe (which bounds this kernel): one warp
     // reduction of the packed word yields the largest high half, one of the word shifted left by 16 (FMA pipe) the largest low
-    // half. The lane's own maximum is only needed when something happens.
+    // half. Which lane and cell hold the maximum is found by searching the anti-diagonal, and only when that is needed.
     auto scan_fast = [&](unsigned best2, const unsigned (&A)[P], int dd, int u, bool tailm) -> bool {   // tailm: constant at every call site
         const unsigned rhi = __reduce_max_sync(FULL, best2);
         const unsigned rlo = __reduce_max_sync(FULL, (unsigned)imad((int)best2, p.k65536, 0));
         int h = (int)(max(rhi, rlo) >> 16);
         if (NW > 1) {
-            if (lane == 0) sm->scan_h[dd & 1][warp] = h;
+            if (lane == 0) sm->scan_h[dd & 3][warp] = h;
             __syncthreads();
-            h = __reduce_max_sync(FULL, lane < NW ? sm->scan_h[dd & 1][lane] : INT_MIN);
+            h = __reduce_max_sync(FULL, lane < NW ? sm->scan_h[dd & 3][lane] : INT_MIN);
         }
         if ((unsigned)(h - thrS) <= (unsigned)Zeff) return false;
-        const int lane_h = (int)max(best2 & 0xffffu, best2 >> 16);
         if (h > thrS) {                                                  // above the window: a new maximum
-            const int ow = owner_warp(h, dd & 1);
-            if (NW == 1 || warp == ow) {
-                const unsigned who = __ballot_sync(FULL, lane_h == h);
-                snap_src = 31 - __clz((int)who);
-                snapshot(A, vm2, tailm);
-            }
+            const int ow = owner_warp(h, dd & 3);
+            if (NW == 1 || warp == ow) snapshot(A, vm2, tailm);
             snap_d = dd; snap_u = u; snap_w = ow; snap_h = h;
             mx_h = h; mx_d = dd;
             thrS = h - Zeff;
             return false;
         }
-        ev_lane_h = lane_h; ev_h = h;
+        ev_h = h;
         return true;
     };
     // mask: 0 none, 1 the tail's valid-cell bits (vm2), 2 prologue -- the cells beyond the near matrix edges (|k| > dd) hold
@@ -458,11 +516,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         resolve();                                                       // the test needs (mt, mq) ...
         sync_state();                                                    // ... and the maximum as a true score
         if (ev_empty) { ev_empty = false; return scan_update(st, INT_MIN, 0, dd, u, p); }   // no cell on this anti-diagonal
-        const int ow = owner_warp(ev_h, dd & 1);
+        const int ow = owner_warp(ev_h, dd & 3);
         int g = 0;
         if (NW == 1 || warp == ow) {
-            const unsigned who = __ballot_sync(FULL, ev_lane_h == ev_h);
-            const int src = 31 - __clz((int)who);
             unsigned m2 = vm2;
             if (mask == 2) {
                 const int k0 = -W + 2 * C * gl + u;
@@ -473,8 +529,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             unsigned B[P];
 #pragma unroll
             for (int jj = 0; jj < P; jj++) B[jj] = mask ? (A[jj] & (unsigned)imad((int)((m2 >> jj) & 0x00010001u), p.m16, 0)) : A[jj];
-            const int jb = __shfl_sync(FULL, search(B, ev_h), src);
-            g = C * (32 * warp + src) + jb;
+            const int jb = search(B, ev_h);
+            const int src = 31 - __clz((int)__ballot_sync(FULL, jb >= 0));
+            g = C * (32 * warp + src) + __shfl_sync(FULL, jb, src);
         }
         g = group_bcast(g, ow);
         return scan_update(st, ev_h - bias + base - D(dd), g, dd, u, p);
@@ -527,7 +584,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
                     // neighbour is the matrix-edge value E(W,0) (agatha_kernel.h:130)
                     if (!PRO) x = FLOORU16 << 16;
                     else x = (unsigned)((dd == W) ? (-(p.goe + p.ge * W) - p.goe + bias + D(W)) : (int)FLOORU16) << 16;
-                } else x = sm->edgeE[warp - 1];
+                } else x = sm->edgeE[((dd - 1) >> 1) & 1][warp - 1];
             }
             const unsigned ein = prmt(x, AE[P - 1], 0x5432);             // lo: neighbour's E[C-1], hi: own E[P-1]
             best2 = cells16<C, 0, TAILM>(A0, AE, AF, Qw, Rw, ein, k, vm2);
@@ -537,12 +594,12 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             // prologue: the matrix-edge cells of this anti-diagonal, BEFORE the hand-over slot is published (an injected E / F
             // at the first or last cell of a warp is read by the neighbouring warp)
             if (PRO) { if (dd < W) inject(dd, u_tag); }
-            if (NW > 1) { if (lane == 0) sm->edgeF[warp] = AF[0]; }
+            if (NW > 1) { if (lane == 0) sm->edgeF[(dd >> 1) & 1][warp] = AF[0]; }
         } else {
             unsigned y = __shfl_down_sync(FULL, AF[0], 1);               // neighbour's (F[0], F[P])
             if (lane == 31) {
                 if (NW == 1 || warp == NW - 1) y = FLOORU16;             // right of the last lane: dead
-                else y = sm->edgeF[warp + 1];
+                else y = sm->edgeF[((dd - 1) >> 1) & 1][warp + 1];
             }
             const unsigned fin = prmt(AF[0], y, 0x5432);                 // lo: own F[P], hi: neighbour's F[0]
             best2 = cells16<C, 1, TAILM>(A1, AE, AF, Qw, Rw, fin, k, vm2);
@@ -551,7 +608,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             if (BLK) shift_query_blk(); else shift_query();
             if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }
             if (PRO) { if (dd < W) inject(dd, u_tag); }
-            if (NW > 1) { if (lane == 31) sm->edgeE[warp] = AE[P - 1]; }
+            if (NW > 1) { if (lane == 31) sm->edgeE[(dd >> 1) & 1][warp] = AE[P - 1]; }
         }
         if (!scan) {                                                     // computed, not scanned (d >= L before the wrap-up)
             if (NW > 1) __syncthreads();
@@ -565,6 +622,116 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             }
         }
         return (U == 0) ? scan_fast(best2, A0, dd, 0, TAILM) : scan_fast(best2, A1, dd, 1, TAILM);
+    };
+
+    // ---- multi-warp groups: the pipelined steady state ---------------------------------------------------------------------
+    // In lock step (step16) a group pays one __syncthreads per anti-diagonal with a serial tail behind it (shared-memory read of
+    // the per-warp maxima, warp reduction, test, then the shuffle and shared-memory read of the neighbour's edge value) while
+    // the ALU pipe idles. Here a warp only ever waits for what it is about to read, and it has published its own part a whole
+    // step earlier:
+    //   * the edge value a step hands to the neighbouring warp does not depend on the edge value coming in during the same
+    //     step (out_edge16), so step d computes it FIRST, publishes it and arrives on the barrier (phase d); only then does it
+    //     wait for phase d-1 -- the neighbours' edge values of d-1, published at the top of THEIR step d-1. A warp can run a
+    //     full anti-diagonal ahead of the slowest one before it has to wait (edge slots are double-buffered for this).
+    //   * per-warp maxima are published at the end of a step and tested TWO steps later: phase d-1 complete means every warp
+    //     has finished step d-2 and published its maximum, and the H values of d-2 are still in the registers step d is about
+    //     to overwrite (new maximum: snapshot as usual; possible Z-drop: saved to shared memory, the cold path looks at them
+    //     after the step). Terminations are therefore noticed a few anti-diagonals late -- results do not depend on cells
+    //     computed after the one that stops the alignment.
+    // The pipeline is entered behind a __syncthreads (pipe_enter) and left through pipe_drain, which tests what is pending.
+    int pipe_lo = 0;                                                     // first anti-diagonal computed by the current pipeline run
+    int ev_d = 0;                                                        // anti-diagonal saved in evsnap
+    auto pipe_enter = [&](int d0) {
+        if (lane == 0) mbar_arrive(&sm->mbar[(d0 - 1) & 1]);             // phase "d0-1": those edge values are published (lock step)
+        pipe_lo = d0;
+    };
+    // test of anti-diagonal dt given the per-warp maxima `v` (lane w < NW: warp w's; INT_MIN elsewhere); A: its H values.
+    // True = it might fire Z-drop (cold path).
+    auto pipe_test = [&](int dt, int v, const unsigned (&A)[P], int u) -> bool {
+        const int h = __reduce_max_sync(FULL, v);
+        thrS += (u == 1) ? dod : de;                                     // into the units of dt
+        if ((unsigned)(h - thrS) <= (unsigned)Zeff) return false;
+        if (h > thrS) {                                                  // a new maximum
+            const int ow = 31 - __clz((int)__ballot_sync(FULL, v == h));
+            if (warp == ow) snapshot(A, 0u, false);
+            snap_d = dt; snap_u = u; snap_w = ow; snap_h = h;
+            mx_h = h; mx_d = dt;
+            thrS = h - Zeff;
+            return false;
+        }
+        ev_h = h;
+        return true;
+    };
+    auto load_maxima = [&](int dt) -> int { return (lane < NW) ? sm->scan_h[dt & 3][lane < NW ? lane : 0] : INT_MIN; };
+    // one steady-state anti-diagonal inside a block; true = the test of dd-2 wants the cold path (its H values are in evsnap;
+    // step dd has been computed all the same)
+    auto pipe_step = [&](int dd, auto u_tag) -> bool {
+        constexpr int U = decltype(u_tag)::value;
+        const int ws = (dd >> 1) & 1, rs = ((dd - 1) >> 1) & 1;          // edge slot this step writes / reads
+        bool slow = false;
+        unsigned best2;
+        if (U == 0) {
+            unsigned x = __shfl_up_sync(FULL, AE[P - 1], 1);
+            const unsigned out = out_edge16<C, 0>(A0, AE, AF, Qw, Rw, k);
+            if (lane == 0) { sm->edgeF[ws][warp] = out; mbar_arrive(&sm->mbar[1]); }      // odd anti-diagonal
+            mbar_wait(&sm->mbar[0], mphase & 1u);
+            mphase ^= 1u;
+            const int v = load_maxima(dd - 2);
+            if (lane == 0) x = (warp == 0) ? (FLOORU16 << 16) : sm->edgeE[rs][warp > 0 ? warp - 1 : 0];
+            if (dd - 2 >= pipe_lo) slow = pipe_test(dd - 2, v, A0, 0);
+            if (slow) { snapshot_ev(A0); ev_d = dd - 2; }
+            const unsigned ein = prmt(x, AE[P - 1], 0x5432);
+            best2 = cells16<C, 0, false>(A0, AE, AF, Qw, Rw, ein, k, 0u);
+            AE[JP] = prmt(AE[JP], floor2, edge_sel);
+            shift_ref_blk();
+        } else {
+            unsigned y = __shfl_down_sync(FULL, AF[0], 1);
+            const unsigned out = out_edge16<C, 1>(A1, AE, AF, Qw, Rw, k);
+            if (lane == 31) { sm->edgeE[ws][warp] = out; mbar_arrive(&sm->mbar[0]); }     // even anti-diagonal
+            mbar_wait(&sm->mbar[1], (mphase >> 1) & 1u);
+            mphase ^= 2u;
+            const int v = load_maxima(dd - 2);
+            if (lane == 31) y = (warp == NW - 1) ? FLOORU16 : sm->edgeF[rs][warp < NW - 1 ? warp + 1 : 0];
+            if (dd - 2 >= pipe_lo) slow = pipe_test(dd - 2, v, A1, 1);
+            if (slow) { snapshot_ev(A1); ev_d = dd - 2; }
+            const unsigned fin = prmt(AF[0], y, 0x5432);
+            best2 = cells16<C, 1, false>(A1, AE, AF, Qw, Rw, fin, k, 0u);
+            AF[JP] = prmt(AF[JP], floor2, edge_sel);
+            shift_query_blk();
+        }
+        const unsigned rhi = __reduce_max_sync(FULL, best2);
+        const unsigned rlo = __reduce_max_sync(FULL, (unsigned)imad((int)best2, p.k65536, 0));
+        // published by the lane that arrives in the NEXT step, so that its arrival orders this write as well
+        if (lane == (U == 0 ? 31 : 0)) sm->scan_h[dd & 3][warp] = (int)(max(rhi, rlo) >> 16);
+        return slow;
+    };
+    // Leave the pipeline in front of step dn (steps up to dn-1 are computed): test what is still pending -- dn-3 if
+    // pipe_step(dn-1) saved it for the cold path (`slow`), then dn-2 and dn-1. True = the alignment stops (d = the anti-diagonal
+    // that fired).
+    int d = 0;
+    bool fired = false;
+    auto pipe_drain = [&](int dn, bool slow) -> bool {
+        {
+            // phase dn-1, the one arrival nobody has waited for yet (every phase is waited for exactly once, whatever happens
+            // below): everybody has finished step dn-2
+            const int b = (dn - 1) & 1;
+            mbar_wait(&sm->mbar[b], (mphase >> b) & 1u);
+            mphase ^= 1u << b;
+        }
+#pragma unroll 1
+        for (int i = slow ? 0 : 1; i < 3; i++) {
+            const int dt = dn - 3 + i;
+            if (i == 2) __syncthreads();                                 // the maxima of dn-1 were published after the last arrival
+            if (dt < pipe_lo) continue;
+            const int u = (dt & 1) ? 0 : 1;                              // W is odd: even anti-diagonals are parity class 1
+            unsigned B[P];
+#pragma unroll
+            for (int jj = 0; jj < P; jj++) B[jj] = (i == 0) ? sm->evsnap[cta_warp][jj][lane] : (u ? A1[jj] : A0[jj]);
+            bool look = true;                                            // i == 0: pipe_test has run (thrS, ev_h are those of dn-3)
+            if (i) look = pipe_test(dt, load_maxima(dt), B, u);
+            if (look) { if (scan_slow(B, dt, u, 0)) { d = dt; fired = true; return true; } }
+        }
+        return false;
     };
 
     // ---- prologue: matrix-edge injection at compile-time positions inside aligned blocks of 8 anti-diagonals ----------------
@@ -612,13 +779,11 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
 
     if (NW > 1) {
         // hand-over slots must describe THIS alignment's initial state before the first step reads them
-        if (lane == 31) sm->edgeE[warp] = AE[P - 1];
-        if (lane == 0) sm->edgeF[warp] = AF[0];
+        if (lane == 31) { sm->edgeE[0][warp] = AE[P - 1]; sm->edgeE[1][warp] = AE[P - 1]; }
+        if (lane == 0) { sm->edgeF[0][warp] = AF[0]; sm->edgeF[1][warp] = AF[0]; }
         __syncthreads();
     }
 
-    int d = 0;
-    bool fired = false;
     using NOBLK = std::integral_constant<int, 0>;
     using INBLK = std::integral_constant<int, 1>;
     // The prologue, d = 0 .. W. Inside it no value can leave the 16-bit range (host-side bound, extend_dispatch.h), so there
@@ -652,19 +817,45 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
 
     bool redo = false, band_exit = false;
     int d_check = -64;                                                   // anti-diagonal of the last range check
-    if (!fired) {
+    // feeds of a steady-state block: 8 query bases (first in the top nibble) and 8 target bases (first in the bottom nibble)
+    auto block_feeds = [&]() {
+        window_pos(d);
+        const int nq = qtop + 1, nb = rbot + C;
+        const uint32_t q0 = load_qword(pr, nq >> 3), q1 = load_qword(pr, (nq >> 3) + 1);
+        const uint32_t t0 = load_tword(pr, nb >> 3), t1 = load_tword(pr, (nb >> 3) + 1);
+        qfeed = __funnelshift_l(q1, q0, 4 * (nq & 7));
+        rfeed = __funnelshift_r(t0, t1, 4 * (nb & 7)) & 0x77777777u;
+    };
+    if constexpr (NW > 1) {
+        // ---- steady state of a multi-warp group: pipelined blocks of 16 anti-diagonals, drained for every range check ----------
+        while (!fired && d + 16 <= d_fast_hi) {
+            if (d - d_check >= 32) { if (!check_range(d)) { redo = true; break; } d_check = d; }
+            pipe_enter(d);                                               // (everybody is behind a barrier here)
+            int ev = 0;
+            for (;;) {
+                block_feeds();
+                const int dblk = d + 16;
+#pragma unroll 1
+                for (; d < dblk; d += 2) {
+                    if (pipe_step(d, U1{})) { ev = 1; break; }
+                    if (pipe_step(d + 1, U0{})) { ev = 2; break; }
+                }
+                if (ev || d + 16 > d_fast_hi || d - d_check >= 32) break;
+            }
+            // cold: out of the pipeline. ev == 1: steps up to d are computed, ev == 2: up to d + 1, no event: up to d - 1.
+            if (pipe_drain(d + ev, ev != 0)) break;
+            if (ev == 1) {
+                // back to an even anti-diagonal in lock step (the feeds of the interrupted block are still in place)
+                if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{}, inject_pro)) { if (scan_slow(A0, d + 1, 0, 0)) { fired = true; d++; break; } }
+            }
+            if (ev) d += 2;
+        }
+        if (!fired && !redo) { window_pos(d); refeed(); }
+    } else if (!fired) {
         // ---- steady state: blocks of 16 anti-diagonals, range check every second block --------------------------------------
         while (d + 16 <= d_fast_hi && !fired && !redo) {
             if (d - d_check >= 32) { if (!check_range(d)) { redo = true; break; } d_check = d; }
-            {
-                // feeds of the block: 8 query bases (first in the top nibble) and 8 target bases (first in the bottom nibble)
-                window_pos(d);
-                const int nq = qtop + 1, nb = rbot + C;
-                const uint32_t q0 = load_qword(pr, nq >> 3), q1 = load_qword(pr, (nq >> 3) + 1);
-                const uint32_t t0 = load_tword(pr, nb >> 3), t1 = load_tword(pr, (nb >> 3) + 1);
-                qfeed = __funnelshift_l(q1, q0, 4 * (nq & 7));
-                rfeed = __funnelshift_r(t0, t1, 4 * (nb & 7)) & 0x77777777u;
-            }
+            block_feeds();
             const int dblk = d + 16;
 #if AGATHA_INLINE_EVENTS
 #pragma unroll 1
@@ -754,6 +945,11 @@ __global__ void __launch_bounds__(Shape16<C, NW>::threads, Shape16<C, NW>::min_b
     const int warp = NW == 1 ? 0 : cta_warp;
     __shared__ Shared16<C, NW> smem;
     Shared16<C, NW>* sm = &smem;
+    unsigned mphase = 0u;                             // NW > 1: bit b = parity of the phase this warp waits for next on barrier b
+    if (NW > 1) {
+        if (threadIdx.x == 0) { mbar_init(&sm->mbar[0], NW); mbar_init(&sm->mbar[1], NW); }
+        __syncthreads();
+    }
     for (;;) {
         unsigned job = 0;
         if (NW == 1) {
@@ -781,7 +977,7 @@ __global__ void __launch_bounds__(Shape16<C, NW>::threads, Shape16<C, NW>::min_b
 
         int score = 0, qend = 0, tend = 0, stop = AGATHA_STOP_END, dstop = 0;
         bool done = true;
-        if (pr.qlen > 0 && pr.tlen > 0) done = run_pair16<C, NW, JWS>(pr, p, lane, warp, cta_warp, sm, score, qend, tend, stop, dstop);
+        if (pr.qlen > 0 && pr.tlen > 0) done = run_pair16<C, NW, JWS>(pr, p, lane, warp, cta_warp, sm, mphase, score, qend, tend, stop, dstop);
         if (lane == 0 && warp == 0) {
             if (done) {
                 ja.score[idx] = score; ja.qend[idx] = qend; ja.tend[idx] = tend;   // agatha_kernel.h:359-363

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -95,6 +96,26 @@ inline void block_barrier()
     const unsigned long long gen = blk.gen;
     if (++blk.arrived == blk.nthreads) { blk.arrived = 0; blk.gen++; }
     else while (blk.gen == gen) yield();
+}
+
+// mbarrier (split arrive / wait): bits 0..15 pending arrivals, 16..31 expected count, bit 32 parity of the current phase
+inline void mbar_init(uint64_t* b, unsigned count) { *b = (uint64_t)count | ((uint64_t)count << 16); }
+inline void mbar_arrive(uint64_t* b)
+{
+    uint64_t v = *b;
+    unsigned pending = (unsigned)(v & 0xffffu) - 1u;
+    const unsigned count = (unsigned)((v >> 16) & 0xffffu);
+    uint64_t phase = (v >> 32) & 1u;
+    if (pending == 0u) { pending = count; phase ^= 1u; }
+    *b = (uint64_t)pending | ((uint64_t)count << 16) | (phase << 32);
+}
+inline void mbar_wait(uint64_t* b, unsigned parity)
+{
+    unsigned long long spins = 0;
+    while ((unsigned)((*(volatile uint64_t*)b >> 32) & 1u) == (parity & 1u)) {
+        if (++spins > 50000000ull) { fprintf(stderr, "emu: mbar_wait never completes (deadlock in the kernel under test)\n"); abort(); }
+        yield();
+    }
 }
 
 }  // namespace emu

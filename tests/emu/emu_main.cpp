@@ -92,12 +92,33 @@ static void run_block(int nthreads, void (*body)(void*), void* arg)
         for (int r = 0; r < 6; r++) *--sp = nullptr;
         f.sp = sp;
     }
+    // Order in which the fibers get their turn: forward (0, default), backward (1) or reshuffled every round (2+: the seed).
+    // Shared-memory protocols between warps (hand-over slots, arrive / wait barriers) must not depend on it.
+    const char* sched_env = getenv("AGATHA_EMU_SCHED");
+    const int sched = sched_env ? atoi(sched_env) : 0;
+    std::vector<int> order(nthreads);
+    for (int t = 0; t < nthreads; t++) order[t] = sched == 1 ? nthreads - 1 - t : t;
+    unsigned long long rng = 0x9e3779b97f4a7c15ull * (unsigned long long)(sched + 1);
     int live = nthreads;
+    unsigned long long round = 0, stalled = 0;      // sched >= 2: warps that get no turn for a while (bit per warp), redrawn every 48 rounds
     while (live) {
         live = 0;
-        for (int t = 0; t < nthreads; t++) {
+        if (sched >= 2 && (round++ % 48) == 0) {
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            stalled = (rng >> 20) & (rng >> 40);                       // about a quarter of the warps
+            if ((stalled & ((1ull << nwarps) - 1ull)) == ((1ull << nwarps) - 1ull)) stalled = 0;
+        }
+        if (sched >= 2) {
+            for (int t = nthreads - 1; t > 0; t--) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[t], order[(int)((rng >> 33) % (unsigned long long)(t + 1))]);
+            }
+        }
+        for (int ti = 0; ti < nthreads; ti++) {
+            const int t = order[ti];
             Fiber& f = fibers[t];
             if (f.done) continue;
+            if (sched >= 2 && ((stalled >> ((t / 32) & 63)) & 1ull)) { live++; continue; }
             g_fiber = &f; cur = &f.th;
             emu_switch(&g_sched_sp, f.sp);
             if (!f.done) live++;
