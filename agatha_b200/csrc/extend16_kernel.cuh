@@ -41,6 +41,12 @@
 #ifndef AGATHA_MBW4
 #define AGATHA_MBW4 3
 #endif
+#ifndef AGATHA_DEADSKIP
+#define AGATHA_DEADSKIP 1        // multi-warp groups: warps without a cell inside the matrix skip the cell update (prologue, tail)
+#endif
+#ifndef AGATHA_ASYNC_RANGE
+#define AGATHA_ASYNC_RANGE 1     // multi-warp groups: range monitor inside the pipeline (0: drain the pipeline for every check)
+#endif
 #ifndef AGATHA_INLINE_EVENTS
 #define AGATHA_INLINE_EVENTS 0
 #endif
@@ -416,7 +422,8 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     };
 
     // ---- range monitor over the live H values (both parities) + re-basing; false = values leave the safe window --------
-    auto check_range = [&](int d_now) -> bool {                         // d_now: the anti-diagonal about to be computed
+    // the warp's part: dead positions pushed back to the floor, minimum and maximum of the warp's live H values
+    auto range_local = [&](int& mn, int& mx) {
         // push the dead positions back to the floor (lanes beyond the band; in the band-edge lane the cells beyond k = +W)
 #pragma unroll
         for (int jj = 0; jj < P; jj++) {
@@ -427,22 +434,35 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
                 AE[jj] = (AE[jj] & k0) | (floor2 & ~k0); AF[jj] = (AF[jj] & k0) | (floor2 & ~k0);
             }
         }
+        // The minimum is taken over the values ABOVE the floor. A cell that holds exactly the floor is not a live value on its
+        // way down (those are caught between the floor and low_ok, the margins see to that): it is the stored MINUS_INF2 -- an
+        // input that the padding-column patch of the tail has just reset, or a cell of a warp that skipped the prologue. Such a
+        // cell must not hand the pair to the general kernel. (x - floor - 1 wraps the floor to 0xffff.)
+        const unsigned off2 = pack16raw(-((int)FLOORU16 + 1), -((int)FLOORU16 + 1));
         unsigned mn2 = 0xffffffffu, mx2 = 0u;
 #pragma unroll
         for (int jj = 0; jj < P; jj++) {
             const unsigned x0 = A0[jj], x1 = A1[jj];
             mx2 = __vimax3_u16x2(mx2, x0, x1);
             const unsigned k0 = keep_mask(jj, false), k1 = keep_mask(jj, true);   // dead cells are out of the minimum
-            mn2 = __vimin3_u16x2(mn2, edge_lane ? (x0 | ~k0) : x0, edge_lane ? (x1 | ~k1) : x1);
+            mn2 = __vimin3_u16x2(mn2, __viaddmax_u16x2(edge_lane ? (x0 | ~k0) : x0, off2, 0u), __viaddmax_u16x2(edge_lane ? (x1 | ~k1) : x1, off2, 0u));
         }
-        int mn = (int)min(mn2 & 0xffffu, mn2 >> 16), mx = (int)max(mx2 & 0xffffu, mx2 >> 16);
-        if (dead_lane) mn = 65535;
+        mn = (int)min(mn2 & 0xffffu, mn2 >> 16) + (int)FLOORU16 + 1; mx = (int)max(mx2 & 0xffffu, mx2 >> 16);
+        if (dead_lane) mn = 65535 + (int)FLOORU16;
         mn = __reduce_min_sync(FULL, mn);
         mx = __reduce_max_sync(FULL, mx);
+    };
+    // what the monitor looks for: true = the full check has something to do (hand-over to the general kernel or re-basing)
+    auto range_alarm = [&](int mn, int mx, int d_now) -> bool {
+        return mn < low_ok || mn - bias + base - D(d_now) < neg_ok || mx > high_ok - 1024;
+    };
+    auto check_range = [&](int d_now) -> bool {                         // d_now: the anti-diagonal about to be computed
+        int mn, mx;
+        range_local(mn, mx);
         if (NW > 1) {
             if (lane == 0) { sm->rng[0][warp] = mn; sm->rng[1][warp] = mx; }
             __syncthreads();
-            mn = __reduce_min_sync(FULL, lane < NW ? sm->rng[0][lane] : 65535);
+            mn = __reduce_min_sync(FULL, lane < NW ? sm->rng[0][lane] : INT_MAX);
             mx = __reduce_max_sync(FULL, lane < NW ? sm->rng[1][lane] : 0);
             __syncthreads();
         }
@@ -564,6 +584,12 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         using UN = std::integral_constant<int, 1 - U>;
         thrS += (U == 1) ? dod : de;                                     // into the units of this anti-diagonal: delta(dd - 1)
         bool empty = false;
+        // Multi-warp groups: a warp none of whose cells lies inside the matrix on this anti-diagonal (prologue: beyond the near
+        // edges, with a margin for the injected matrix-edge cells; tail: beyond the far edges) skips the cell update. Nothing
+        // inside the matrix ever reads such cells; the warp keeps shifting its sequence windows and stays in lock step.
+        bool wdead = false;
+        const int wk_lo = -W + 2 * C * 32 * warp, wk_hi = wk_lo + 2 * C * 32 - 1;      // diagonals owned by this warp
+        if (AGATHA_DEADSKIP && NW > 1 && PRO) wdead = (wk_lo > dd + 3) || (wk_hi < -(dd + 3));
         if (TAILM) {
             // cells of this anti-diagonal inside the matrix (padding columns count: agatha_kernel.h CORE_COMPUTE has no r < tlen guard)
             const int klo = max(-W, max(-dd, dd - 2 * (pr.qlen - 1)));
@@ -574,8 +600,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             vm2 = (fm & ((1u << P) - 1u)) | ((fm >> P) << 16);
             // no cell at all: parity of the valid range included (k has the parity of dd)
             empty = ((khi - ((khi ^ dd) & 1)) < (klo + ((klo ^ dd) & 1)));
+            if (AGATHA_DEADSKIP && NW > 1) wdead = (wk_lo > khi) || (wk_hi < klo);
         }
-        unsigned best2;
+        unsigned best2 = 0u;
         if (U == 0) {
             unsigned x = __shfl_up_sync(FULL, AE[P - 1], 1);             // neighbour's (E[P-1], E[C-1])
             if (lane == 0) {
@@ -587,13 +614,15 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
                 } else x = sm->edgeE[((dd - 1) >> 1) & 1][warp - 1];
             }
             const unsigned ein = prmt(x, AE[P - 1], 0x5432);             // lo: neighbour's E[C-1], hi: own E[P-1]
-            best2 = cells16<C, 0, TAILM>(A0, AE, AF, Qw, Rw, ein, k, vm2);
-            AE[JP] = prmt(AE[JP], floor2, edge_sel);                    // band-edge lane: nothing leaks into k = W+1
+            if (!wdead) {
+                best2 = cells16<C, 0, TAILM>(A0, AE, AF, Qw, Rw, ein, k, vm2);
+                AE[JP] = prmt(AE[JP], floor2, edge_sel);                // band-edge lane: nothing leaks into k = W+1
+            }
             if (BLK) shift_ref_blk(); else shift_ref();
             if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }   // inputs of the next anti-diagonal
             // prologue: the matrix-edge cells of this anti-diagonal, BEFORE the hand-over slot is published (an injected E / F
             // at the first or last cell of a warp is read by the neighbouring warp)
-            if (PRO) { if (dd < W) inject(dd, u_tag); }
+            if (PRO) { if (dd < W && !wdead) inject(dd, u_tag); }
             if (NW > 1) { if (lane == 0) sm->edgeF[(dd >> 1) & 1][warp] = AF[0]; }
         } else {
             unsigned y = __shfl_down_sync(FULL, AF[0], 1);               // neighbour's (F[0], F[P])
@@ -602,12 +631,14 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
                 else y = sm->edgeF[((dd - 1) >> 1) & 1][warp + 1];
             }
             const unsigned fin = prmt(AF[0], y, 0x5432);                 // lo: own F[P], hi: neighbour's F[0]
-            best2 = cells16<C, 1, TAILM>(A1, AE, AF, Qw, Rw, fin, k, vm2);
-            // k = +W reads MINUS_INF2 from outside the band; in the prologue that cell is dead until F(0,W) is injected
-            if (!PRO) AF[JP] = prmt(AF[JP], floor2, edge_sel);
+            if (!wdead) {
+                best2 = cells16<C, 1, TAILM>(A1, AE, AF, Qw, Rw, fin, k, vm2);
+                // k = +W reads MINUS_INF2 from outside the band; in the prologue that cell is dead until F(0,W) is injected
+                if (!PRO) AF[JP] = prmt(AF[JP], floor2, edge_sel);
+            }
             if (BLK) shift_query_blk(); else shift_query();
             if (TAILM) { if (has_phantom) phantom_patch16(dd + 1, UN{}); }
-            if (PRO) { if (dd < W) inject(dd, u_tag); }
+            if (PRO) { if (dd < W && !wdead) inject(dd, u_tag); }
             if (NW > 1) { if (lane == 31) sm->edgeE[(dd >> 1) & 1][warp] = AE[P - 1]; }
         }
         if (!scan) {                                                     // computed, not scanned (d >= L before the wrap-up)
@@ -827,28 +858,48 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         rfeed = __funnelshift_r(t0, t1, 4 * (nb & 7)) & 0x77777777u;
     };
     if constexpr (NW > 1) {
-        // ---- steady state of a multi-warp group: pipelined blocks of 16 anti-diagonals, drained for every range check ----------
+        // ---- steady state of a multi-warp group: pipelined blocks of 16 anti-diagonals ------------------------------------------
+        // The range monitor does not interrupt the pipeline: every second block each warp pushes its dead positions back, takes
+        // the minimum / maximum of its own live values and publishes them; two anti-diagonals later (everybody has published by
+        // then, and 32 + 2 anti-diagonals is what the margins of low_ok / high_ok cover) the group-wide values are looked at. Only
+        // when they call for a re-basing or a hand-over does the group leave the pipeline for the full check (check_range).
         while (!fired && d + 16 <= d_fast_hi) {
             if (d - d_check >= 32) { if (!check_range(d)) { redo = true; break; } d_check = d; }
             pipe_enter(d);                                               // (everybody is behind a barrier here)
             int ev = 0;
+            bool rng_pending = false;
             for (;;) {
+                if (AGATHA_ASYNC_RANGE && d - d_check >= 32) {
+                    int mn, mx;
+                    range_local(mn, mx);
+                    if (lane == 31) { sm->rng[0][warp] = mn; sm->rng[1][warp] = mx; }   // lane 31 arrives next (even anti-diagonal)
+                    rng_pending = true;
+                    d_check = d;
+                }
                 block_feeds();
                 const int dblk = d + 16;
 #pragma unroll 1
                 for (; d < dblk; d += 2) {
                     if (pipe_step(d, U1{})) { ev = 1; break; }
                     if (pipe_step(d + 1, U0{})) { ev = 2; break; }
+                    if (rng_pending) {                                   // the wait of step d+1 is behind us: every warp's values are there
+                        rng_pending = false;
+                        const int mn = __reduce_min_sync(FULL, lane < NW ? sm->rng[0][lane < NW ? lane : 0] : INT_MAX);
+                        const int mx = __reduce_max_sync(FULL, lane < NW ? sm->rng[1][lane < NW ? lane : 0] : 0);
+                        if (range_alarm(mn, mx, d_check)) { ev = 3; d += 2; break; }
+                    }
                 }
-                if (ev || d + 16 > d_fast_hi || d - d_check >= 32) break;
+                if (ev || d + 16 > d_fast_hi) break;
+                if (!AGATHA_ASYNC_RANGE && d - d_check >= 32) break;
             }
-            // cold: out of the pipeline. ev == 1: steps up to d are computed, ev == 2: up to d + 1, no event: up to d - 1.
-            if (pipe_drain(d + ev, ev != 0)) break;
+            // cold: out of the pipeline. ev == 1: steps up to d are computed, ev == 2: up to d + 1, otherwise up to d - 1.
+            if (pipe_drain(d + (ev < 3 ? ev : 0), ev == 1 || ev == 2)) break;
             if (ev == 1) {
                 // back to an even anti-diagonal in lock step (the feeds of the interrupted block are still in place)
                 if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{}, inject_pro)) { if (scan_slow(A0, d + 1, 0, 0)) { fired = true; d++; break; } }
             }
-            if (ev) d += 2;
+            if (ev == 1 || ev == 2) d += 2;
+            if (ev == 3 || rng_pending) d_check = d - 32;                // the full check, now
         }
         if (!fired && !redo) { window_pos(d); refeed(); }
     } else if (!fired) {

@@ -1104,7 +1104,9 @@ struct KernelShape {
 
 // Redo mode (template parameter REDO, JobArrays::redo says which instance the host launches): the packed kernel (extend16_kernel.cuh) ran first and marked the pairs it could not finish with
 // REDO_MARK in their query-end slot; this kernel then looks at every pair, 32 candidates per queue access, and aligns the
-// marked ones. A launch without marked pairs costs a few microseconds.
+// marked ones. The 32 candidates of one access are spread over the whole (longest-first) order -- positions c, c + n/32,
+// c + 2n/32, ... -- because marked pairs come in runs (every pair not longer than the band sits at the end of the order) and a
+// run must not end up in one group. A launch without marked pairs costs a few microseconds.
 constexpr int REDO_MARK = INT_MIN;
 
 template <int C, int NW, bool WODD, int JWS, bool REDO = false>
@@ -1116,8 +1118,9 @@ __global__ void __launch_bounds__(KernelShape<C, NW>::threads, KernelShape<C, NW
     GroupShared<NW>* sm = reinterpret_cast<GroupShared<NW>*>(&smem);
     // (REDO is a template parameter, not a run-time mode: the plain kernel keeps exactly the loop it always had)
     unsigned todo = 0, cand_idx = 0;
+    const unsigned n_chunks = ((unsigned)ja.n + 31u) / 32u;            // redo mode: queue positions
     for (;;) {
-        const unsigned step = (REDO && !todo) ? 32u : 1u;
+        const unsigned step = 1u;
         unsigned job = 0;
         if (!REDO || !todo) {                          // next queue position, uniform across the group
             if (NW == 1) {
@@ -1129,14 +1132,14 @@ __global__ void __launch_bounds__(KernelShape<C, NW>::threads, KernelShape<C, NW
                 __syncthreads();
                 job = sm->job;
             }
-            if (job >= (unsigned)ja.n) break;
+            if (job >= (REDO ? n_chunks : (unsigned)ja.n)) break;
         } else if (NW > 1) __syncthreads();           // the next alignment re-initialises the group's shared slots
         unsigned idx;
         if (!REDO) {
             idx = ja.order ? __ldg(ja.order + job) : job;
         } else {
             if (!todo) {
-                const unsigned cand = job + (unsigned)lane;
+                const unsigned cand = job + (unsigned)lane * n_chunks;
                 bool marked = false;
                 if (cand < (unsigned)ja.n) {
                     cand_idx = ja.order ? __ldg(ja.order + cand) : cand;
