@@ -423,7 +423,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
 
     // ---- range monitor over the live H values (both parities) + re-basing; false = values leave the safe window --------
     // the warp's part: dead positions pushed back to the floor, minimum and maximum of the warp's live H values
-    auto range_local = [&](int& mn, int& mx) {
+    // floor_tag: whether cells at the stored floor can occur among the live ones (tail, multi-warp groups) -- see below
+    auto range_local = [&](int& mn, int& mx, auto floor_tag) {
+        constexpr bool FLOORS = decltype(floor_tag)::value != 0;
         // push the dead positions back to the floor (lanes beyond the band; in the band-edge lane the cells beyond k = +W)
 #pragma unroll
         for (int jj = 0; jj < P; jj++) {
@@ -437,7 +439,8 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         // The minimum is taken over the values ABOVE the floor. A cell that holds exactly the floor is not a live value on its
         // way down (those are caught between the floor and low_ok, the margins see to that): it is the stored MINUS_INF2 -- an
         // input that the padding-column patch of the tail has just reset, or a cell of a warp that skipped the prologue. Such a
-        // cell must not hand the pair to the general kernel. (x - floor - 1 wraps the floor to 0xffff.)
+        // cell must not hand the pair to the general kernel. (x - floor - 1 wraps the floor to 0xffff.) The steady state of a
+        // one-warp group has neither (FLOORS false): plain minimum.
         const unsigned off2 = pack16raw(-((int)FLOORU16 + 1), -((int)FLOORU16 + 1));
         unsigned mn2 = 0xffffffffu, mx2 = 0u;
 #pragma unroll
@@ -445,9 +448,11 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             const unsigned x0 = A0[jj], x1 = A1[jj];
             mx2 = __vimax3_u16x2(mx2, x0, x1);
             const unsigned k0 = keep_mask(jj, false), k1 = keep_mask(jj, true);   // dead cells are out of the minimum
-            mn2 = __vimin3_u16x2(mn2, __viaddmax_u16x2(edge_lane ? (x0 | ~k0) : x0, off2, 0u), __viaddmax_u16x2(edge_lane ? (x1 | ~k1) : x1, off2, 0u));
+            const unsigned y0 = edge_lane ? (x0 | ~k0) : x0, y1 = edge_lane ? (x1 | ~k1) : x1;
+            if (FLOORS) mn2 = __vimin3_u16x2(mn2, __viaddmax_u16x2(y0, off2, 0u), __viaddmax_u16x2(y1, off2, 0u));
+            else mn2 = __vimin3_u16x2(mn2, y0, y1);
         }
-        mn = (int)min(mn2 & 0xffffu, mn2 >> 16) + (int)FLOORU16 + 1; mx = (int)max(mx2 & 0xffffu, mx2 >> 16);
+        mn = (int)min(mn2 & 0xffffu, mn2 >> 16) + (FLOORS ? (int)FLOORU16 + 1 : 0); mx = (int)max(mx2 & 0xffffu, mx2 >> 16);
         if (dead_lane) mn = 65535 + (int)FLOORU16;
         mn = __reduce_min_sync(FULL, mn);
         mx = __reduce_max_sync(FULL, mx);
@@ -456,9 +461,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     auto range_alarm = [&](int mn, int mx, int d_now) -> bool {
         return mn < low_ok || mn - bias + base - D(d_now) < neg_ok || mx > high_ok - 1024;
     };
-    auto check_range = [&](int d_now) -> bool {                         // d_now: the anti-diagonal about to be computed
+    auto check_range = [&](int d_now, auto floor_tag) -> bool {         // d_now: the anti-diagonal about to be computed
         int mn, mx;
-        range_local(mn, mx);
+        range_local(mn, mx, floor_tag);
         if (NW > 1) {
             if (lane == 0) { sm->rng[0][warp] = mn; sm->rng[1][warp] = mx; }
             __syncthreads();
@@ -864,14 +869,14 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         // then, and 32 + 2 anti-diagonals is what the margins of low_ok / high_ok cover) the group-wide values are looked at. Only
         // when they call for a re-basing or a hand-over does the group leave the pipeline for the full check (check_range).
         while (!fired && d + 16 <= d_fast_hi) {
-            if (d - d_check >= 32) { if (!check_range(d)) { redo = true; break; } d_check = d; }
+            if (d - d_check >= 32) { if (!check_range(d, S1{})) { redo = true; break; } d_check = d; }
             pipe_enter(d);                                               // (everybody is behind a barrier here)
             int ev = 0;
             bool rng_pending = false;
             for (;;) {
                 if (AGATHA_ASYNC_RANGE && d - d_check >= 32) {
                     int mn, mx;
-                    range_local(mn, mx);
+                    range_local(mn, mx, S1{});
                     if (lane == 31) { sm->rng[0][warp] = mn; sm->rng[1][warp] = mx; }   // lane 31 arrives next (even anti-diagonal)
                     rng_pending = true;
                     d_check = d;
@@ -905,7 +910,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     } else if (!fired) {
         // ---- steady state: blocks of 16 anti-diagonals, range check every second block --------------------------------------
         while (d + 16 <= d_fast_hi && !fired && !redo) {
-            if (d - d_check >= 32) { if (!check_range(d)) { redo = true; break; } d_check = d; }
+            if (d - d_check >= 32) { if (!check_range(d, S0{})) { redo = true; break; } d_check = d; }
             block_feeds();
             const int dblk = d + 16;
 #if AGATHA_INLINE_EVENTS
@@ -950,7 +955,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         int next_slice = ((d + span - 1) / span) * span;
         if (has_phantom) phantom_patch16(d, U1{});                       // inputs of the first tail step
         while (d < d_end && !fired && !redo && !band_exit) {
-            if (d - d_check >= 32) { if (!check_range(d)) { redo = true; break; } d_check = d; }
+            if (d - d_check >= 32) { if (!check_range(d, S1{})) { redo = true; break; } d_check = d; }
             const int dchunk = min(d_end, d_check + 32);
             int ev = 0;
 #pragma unroll 1

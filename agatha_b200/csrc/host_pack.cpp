@@ -4,6 +4,7 @@
 // pack_kernel (pack_kernel.cuh): every sequence starts at a multiple of 8 bases and is padded to a multiple of 8 with 'N';
 // query words carry their first base in the top nibble, target words in the bottom nibble. The per-sequence op byte
 // (bit 0 reverse, bit 1 complement; test_prog.cpp:83-92) is applied on the way, which replaces apply_ops_kernel on this path.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <immintrin.h>
@@ -69,15 +70,8 @@ __attribute__((target("avx2"))) static uint32_t pack_avx2(const uint8_t* src, ui
 
 static const bool g_avx2 = __builtin_cpu_supports("avx2");
 
-}  // namespace agatha
-
-using namespace agatha;
-
-extern "C" int agatha_pack_batch(const uint8_t* bases, const uint64_t* offsets, const uint32_t* lens, const uint64_t* ids, const uint8_t* ops,
-                                 uint64_t n, int32_t is_target, uint32_t* dst_words, uint64_t dst_capacity_words,
-                                 uint32_t* dst_offsets, uint32_t* dst_lens, uint64_t* bases_out, int32_t n_threads)
+int pack_layout(const uint32_t* lens, const uint64_t* ids, uint64_t n, uint64_t dst_capacity_words, uint32_t* dst_offsets, uint32_t* dst_lens, uint64_t* bases_out)
 {
-    if (!bases || !offsets || !lens || !dst_words || !dst_offsets) return set_error(AGATHA_EINVAL, "NULL argument");
     uint64_t o = 0;
     for (uint64_t j = 0; j < n; j++) {
         const uint64_t id = ids ? ids[j] : j;
@@ -88,19 +82,44 @@ extern "C" int agatha_pack_batch(const uint8_t* bases, const uint64_t* offsets, 
     }
     if (o == 0) o = 8;
     if (o / 8 > dst_capacity_words) return set_error(AGATHA_EINVAL, "packed staging buffer too small: need %llu words, have %llu", (unsigned long long)(o / 8), (unsigned long long)dst_capacity_words);
-    if (n == 0 || (n == 1 && lens[ids ? ids[0] : 0] == 0)) pack_scalar(bases, 0, 0, 1, is_target != 0, 0, dst_words);
-    if (n_threads <= 0) n_threads = 4;
-#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
-    for (int64_t j = 0; j < (int64_t)n; j++) {
-        const uint64_t id = ids ? ids[j] : (uint64_t)j;
-        const uint32_t len = lens[id];
-        const unsigned op = ops ? (ops[id] & 3u) : 0u;
-        const uint8_t* src = bases + offsets[id];
-        uint32_t* d = dst_words + (dst_offsets[j] >> 3);
+    if (bases_out) *bases_out = o;
+    return AGATHA_OK;
+}
+
+void pack_range(const PackView& v, uint64_t j0, uint64_t j1)
+{
+    for (uint64_t j = j0; j < j1; j++) {
+        const uint64_t id = v.ids ? v.ids[j] : j;
+        const uint32_t len = v.lens[id];
+        const unsigned op = v.ops ? (v.ops[id] & 3u) : 0u;
+        const uint8_t* src = v.bases + v.offsets[id];
+        uint32_t* d = v.dst_words + (v.dst_offsets[j] >> 3);
         uint32_t done = 0;
-        if (op == 0 && g_avx2) done = pack_avx2(src, len, is_target != 0, d);
-        pack_scalar(src, len, done, (len + 7u) / 8u, is_target != 0, op, d);
+        if (op == 0 && g_avx2) done = pack_avx2(src, len, v.is_target != 0, d);
+        pack_scalar(src, len, done, (len + 7u) / 8u, v.is_target != 0, op, d);
     }
+}
+
+void pack_empty(int is_target, uint32_t* dst_words) { pack_scalar(nullptr, 0, 0, 1, is_target != 0, 0, dst_words); }
+
+}  // namespace agatha
+
+using namespace agatha;
+
+extern "C" int agatha_pack_batch(const uint8_t* bases, const uint64_t* offsets, const uint32_t* lens, const uint64_t* ids, const uint8_t* ops,
+                                 uint64_t n, int32_t is_target, uint32_t* dst_words, uint64_t dst_capacity_words,
+                                 uint32_t* dst_offsets, uint32_t* dst_lens, uint64_t* bases_out, int32_t n_threads)
+{
+    if (!bases || !offsets || !lens || !dst_words || !dst_offsets) return set_error(AGATHA_EINVAL, "NULL argument");
+    uint64_t o = 0;
+    int rc = pack_layout(lens, ids, n, dst_capacity_words, dst_offsets, dst_lens, &o);
+    if (rc) return rc;
+    if (n == 0 || (n == 1 && lens[ids ? ids[0] : 0] == 0)) pack_empty(is_target, dst_words);
+    if (n_threads <= 0) n_threads = 4;
+    const PackView v{bases, offsets, lens, ids, ops, is_target, dst_words, dst_offsets};
+    const int64_t n_chunks = (int64_t)((n + 15) / 16);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
+    for (int64_t c = 0; c < n_chunks; c++) pack_range(v, (uint64_t)c * 16, std::min<uint64_t>(n, (uint64_t)c * 16 + 16));
     if (bases_out) *bases_out = o;
     return AGATHA_OK;
 }

@@ -6,8 +6,10 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <numeric>
@@ -45,6 +47,75 @@ void pool_put(int device, agatha_stream_t* s)
 
 struct Batch { agatha_stream_t* s = nullptr; std::vector<uint64_t> ids; bool busy = false; };
 
+// The packing threads of one device worker. Threads SLEEP between batches (condition variable): with one process per GPU on
+// one box there are as many of these pools as GPUs, next to the CUDA driver's and the caller's own threads, and an OpenMP
+// team's spinning waiters (libgomp's default) take the cores the other ranks' packers need -- measured here: the same
+// packing loop got slower with every thread added once the waiters of several teams had to share cores.
+class PackPool {
+public:
+    explicit PackPool(int n_threads)
+    {
+        for (int i = 1; i < n_threads; i++) threads_.emplace_back([this] { loop(); });
+    }
+    ~PackPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_work_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    // fn(first, last) over [0, n) in chunks; the calling thread works too; returns when everything is done
+    void run(uint64_t n, uint64_t chunk, const std::function<void(uint64_t, uint64_t)>& fn)
+    {
+        if (n == 0) return;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; n_ = n; chunk_ = std::max<uint64_t>(chunk, 1); next_.store(0, std::memory_order_relaxed);
+            pending_ = (int)threads_.size();
+            gen_++;
+        }
+        cv_work_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void work()
+    {
+        for (;;) {
+            const uint64_t at = next_.fetch_add(chunk_, std::memory_order_relaxed);
+            if (at >= n_) break;
+            (*fn_)(at, std::min(n_, at + chunk_));
+        }
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) cv_done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(uint64_t, uint64_t)>* fn_ = nullptr;
+    uint64_t n_ = 0, chunk_ = 1, gen_ = 0;
+    std::atomic<uint64_t> next_{0};
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
 struct Worker {
     int device = 0;
     std::vector<uint64_t> pairs;       // pair indices of this device, most expensive first
@@ -66,18 +137,28 @@ struct JobView {
 
 // Stage one batch with gasal_host_batch_fill's layout (host_batch.cpp:79-154: each sequence at a multiple of 8, padded with
 // 'N') but already in the packed device format, per-pair ops applied on the way: half the H2D bytes, no pack kernel.
-int fill_batch(Batch& b, const JobView& jv, int fill_threads, uint64_t& qbases, uint64_t& tbases)
+int fill_batch(Batch& b, const JobView& jv, PackPool& pool, uint64_t& qbases, uint64_t& tbases)
 {
     const uint64_t n = b.ids.size();
     const uint64_t qtot = agatha_staged_bytes(jv.ql, b.ids.data(), n), ttot = agatha_staged_bytes(jv.tl, b.ids.data(), n);
     if (qtot > 0xfffffff8ull || ttot > 0xfffffff8ull) return set_error(AGATHA_EINVAL, "batch exceeds 4 GiB of bases; lower batch_alns");
     int rc = agatha_stream_reserve(b.s, (uint32_t)n, qtot, ttot);
     if (rc) return rc;
-    rc = agatha_pack_batch(jv.qb, jv.qo, jv.ql, b.ids.data(), jv.qops, n, 0, agatha_stream_query_packed(b.s), qtot / 8,
-                           agatha_stream_query_offsets(b.s), agatha_stream_query_lens(b.s), &qbases, fill_threads);
+    rc = pack_layout(jv.ql, b.ids.data(), n, qtot / 8, agatha_stream_query_offsets(b.s), agatha_stream_query_lens(b.s), &qbases);
     if (rc) return rc;
-    return agatha_pack_batch(jv.tb, jv.to, jv.tl, b.ids.data(), jv.tops, n, 1, agatha_stream_target_packed(b.s), ttot / 8,
-                             agatha_stream_target_offsets(b.s), agatha_stream_target_lens(b.s), &tbases, fill_threads);
+    rc = pack_layout(jv.tl, b.ids.data(), n, ttot / 8, agatha_stream_target_offsets(b.s), agatha_stream_target_lens(b.s), &tbases);
+    if (rc) return rc;
+    const PackView qv{jv.qb, jv.qo, jv.ql, b.ids.data(), jv.qops, 0, agatha_stream_query_packed(b.s), agatha_stream_query_offsets(b.s)};
+    const PackView tv{jv.tb, jv.to, jv.tl, b.ids.data(), jv.tops, 1, agatha_stream_target_packed(b.s), agatha_stream_target_offsets(b.s)};
+    // a batch without a single base still uploads one word: make it padding (a batch of one short sequence overwrites it)
+    if (qbases == 8) pack_empty(0, agatha_stream_query_packed(b.s));
+    if (tbases == 8) pack_empty(1, agatha_stream_target_packed(b.s));
+    // one pass over both sides of the batch: items [0, n) are the reads, [n, 2n) the reference windows
+    pool.run(2 * n, 16, [&](uint64_t a, uint64_t e) {
+        if (a < n) pack_range(qv, a, std::min(e, n));
+        if (e > n) pack_range(tv, std::max(a, n) - n, e - n);
+    });
+    return AGATHA_OK;
 }
 
 void collect(Batch& b, const JobView& jv, Worker& w)
@@ -121,8 +202,12 @@ void run_worker(Worker& w, const JobView& jv, uint32_t batch_alns, int n_streams
             if (rc) fail(rc);
         }
     }
+    PackPool pool(fill_threads);
     size_t next = 0;
     int cur = 0;
+    // The first batches are small (1/8, 1/4, 1/2 of batch_alns): the device starts after an eighth of a batch has been packed
+    // instead of a whole one -- with the longest pairs first that is most of what the job waits for before its first kernel.
+    uint32_t ramp = std::max<uint32_t>(batch_alns / 8, std::min<uint32_t>(batch_alns, 256));
     while (w.rc == AGATHA_OK && next < w.pairs.size()) {
         Batch& b = bs[(size_t)cur];
         if (b.busy) {                                  // oldest batch of this slot: wait for it, then reuse its buffers
@@ -130,11 +215,12 @@ void run_worker(Worker& w, const JobView& jv, uint32_t batch_alns, int n_streams
             if (rc) { fail(rc); break; }
             collect(b, jv, w);
         }
-        const size_t cnt = std::min<size_t>(batch_alns, w.pairs.size() - next);
+        const size_t cnt = std::min<size_t>(std::min(ramp, batch_alns), w.pairs.size() - next);
+        ramp = ramp >= batch_alns / 2 ? batch_alns : ramp * 2;
         b.ids.assign(w.pairs.begin() + (long)next, w.pairs.begin() + (long)(next + cnt));
         next += cnt;
         uint64_t qbytes = 0, tbytes = 0;
-        int rc = fill_batch(b, jv, fill_threads, qbytes, tbytes);
+        int rc = fill_batch(b, jv, pool, qbytes, tbytes);
         if (!rc) rc = agatha_stream_submit_packed(b.s, qbytes, tbytes, (uint32_t)cnt, jv.params);
         if (rc) { fail(rc); break; }
         b.busy = true;
@@ -198,12 +284,15 @@ extern "C" int agatha_align_job(const uint8_t* query_bases, const uint64_t* quer
         std::vector<Key> keys(n_alns);
         const int64_t W = params->band_width;
         const uint64_t width = 2 * (uint64_t)std::max<int64_t>(W, 0) + 1;
-#pragma omp parallel for schedule(static)
+        // (explicit thread counts: launchers such as torchrun export OMP_NUM_THREADS=1, which would make this serial)
+        const int sort_threads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), (cfg && cfg->staging_threads > 0) ? (unsigned)(cfg->staging_threads * ndev) : 8u));
+#pragma omp parallel for schedule(static) num_threads(sort_threads)
         for (int64_t i = 0; i < (int64_t)n_alns; i++) {
             const uint64_t lo = std::min(query_lens[i], target_lens[i]), hi = std::max(query_lens[i], target_lens[i]);
             keys[(size_t)i] = {lo * std::min<uint64_t>(width, hi) + 64, (uint64_t)i};
         }
-        __gnu_parallel::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.cost != b.cost ? a.cost > b.cost : a.idx < b.idx; });
+        __gnu_parallel::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.cost != b.cost ? a.cost > b.cost : a.idx < b.idx; },
+                             __gnu_parallel::default_parallel_tag((unsigned)sort_threads));
         std::vector<uint64_t> load((size_t)ndev, 0);
         for (auto& w : workers) w.pairs.reserve(n_alns / (size_t)ndev + 16);
         for (const Key& k : keys) {

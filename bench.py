@@ -358,6 +358,7 @@ def main():
     ap.add_argument("--ref-gpu-pairs", type=int, default=16384)
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the C1/C3/C4 kernel legs at N = 1")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--staging-threads", type=int, default=0, help="host packing threads per rank in the end-to-end leg (default: the cores of this rank, at most 8)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -441,7 +442,9 @@ def main():
     # ---- e2e leg: host buffers through the C ABI (host packing into pinned staging + H2D + kernels + D2H [+ gather]) ---------
     e2e_steps = max(1, min(args.steps, 3))
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    stg = max(1, min(8, (os.cpu_count() or 8) // max(1, local_world)))          # host staging threads of this rank
+    # host packing threads of this rank: the cores this process may run on (its slice at N > 1), at most 8
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8) // max(1, local_world)
+    stg = args.staging_threads or max(1, min(8, avail))
     p = ag.make_params(**params)
     job = lambda: ag.align_job(data["qbuf"], data["qoff"], qlen, data["tbuf"], data["toff"], tlen, p, devices=[local_rank], staging_threads=stg)
     job()                                                                        # warm-up (allocations)
