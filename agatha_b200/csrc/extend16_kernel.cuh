@@ -321,25 +321,25 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     // window positions as a function of the anti-diagonal about to be computed (even d)
     auto window_pos = [&](int dd) { qtop = ((dd + W) >> 1) - C * gl; rbot = ((dd - W + 1) >> 1) + C * gl; };
 
-    // run-time cell index -> compare + select of a PRMT selector per register; j < 0 (another lane's cell) changes nothing
-    auto poke16 = [&](unsigned (&A)[P], int j, unsigned v2) {
+    // Cell g of the group (g = C * lane + cell; the same number in every lane) takes the value v2: the register is a
+    // warp-uniform choice, which lane and which half goes into one PRMT selector. g outside the group changes nothing.
+    auto poke16 = [&](unsigned (&A)[P], int g, unsigned v2) {
+        const int owner = g >= 0 ? g / C : -1, j = g - owner * C;
+        const int jr = j >= P ? j - P : j;
+        const unsigned sel = (gl == owner) ? (j >= P ? 0x7610u : 0x3254u) : 0x3210u;
 #pragma unroll
-        for (int jj = 0; jj < P; jj++) {
-            const unsigned sel = (j == jj) ? 0x3254u : ((j == jj + P) ? 0x7610u : 0x3210u);
-            A[jj] = prmt(A[jj], v2, sel);
-        }
+        for (int jj = 0; jj < P; jj++) if (jj == jr) A[jj] = prmt(A[jj], v2, sel);
     };
-    auto own = [&](int g) { const int j = g - C * gl; return (j >= 0 && j < C) ? j : -1; };
 
     // ---- boundary: H(-1,-1) = 0 and the virtual cells of "anti-diagonal -1" (agatha_kernel.h:126-148) -------------------
     {
         // H(-1,-1) = 0 is read as the diagonal of step 0 (units of anti-diagonal -2); H(-1,0) = H(0,-1) = -goe as diagonals of
         // step 1 (units of -1); F(0,0) = E(0,0) = -2 goe as gap inputs of step 0 (units of 0)
         const int hv = -p.goe + bias + D(-1), gv = -2 * p.goe + bias + D(0);
-        poke16(A1, own(W >> 1), pk(0 + bias + D(-2)));                 // k = 0 belongs to parity 1 (W odd)
-        const int jt = own((W + 1) >> 1);                              // top: (q=-1, r=0) at k = 1
+        poke16(A1, W >> 1, pk(0 + bias + D(-2)));                      // k = 0 belongs to parity 1 (W odd)
+        const int jt = (W + 1) >> 1;                                   // top: (q=-1, r=0) at k = 1
         poke16(A0, jt, pk(hv)); poke16(AF, jt, pk(gv));
-        const int jl = own((W - 1) >> 1);                              // left: (q=0, r=-1) at k = -1
+        const int jl = (W - 1) >> 1;                                   // left: (q=0, r=-1) at k = -1
         poke16(A0, jl, pk(hv)); poke16(AE, jl, pk(gv));
     }
 
@@ -574,9 +574,10 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         const unsigned v2 = floor2;                                      // MINUS_INF2 (file header)
         const int g = (k + W - U) >> 1;
         const int gf = (U == 0) ? g : g + 1;                             // its F input: U==0 reads F[j], U==1 reads F[j+1]
-        poke16(AF, own(gf), v2);
-        if (r - 1 >= pr.tlen) { if (U == 0) poke16(A0, own(g), v2); else poke16(A1, own(g), v2); }
+        poke16(AF, gf, v2);
+        if (r - 1 >= pr.tlen) { if (U == 0) poke16(A0, g, v2); else poke16(A1, g, v2); }
     };
+
 
     // ---- one packed anti-diagonal; true = scan_slow must look at it ---------------------------------------------------------
     // MODE 0 steady state (every in-band cell inside the matrix); 1 prologue (d <= W: what lies beyond the matrix edges is
@@ -953,6 +954,10 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         const int wrap_lo = wrap ? 8 * pr.total : INT_MAX;
         const int d_end = wrap ? 8 * pr.total + 8 : min(pr.L, 8 * n_slices * p.sw);   // nothing observable beyond
         int next_slice = ((d + span - 1) / span) * span;
+        // (Measured alternatives, both slower on every workload: the patch outside the loop -- the loop leaves for cold code at
+        // every anti-diagonal that needs it, up to 7 in every 8 * slice_width -- and a loop of single steps with everything
+        // special between two runs. Leaving a hot loop costs more instruction fetch than the patch code costs inside it; what
+        // did help is the patch's cheaper poke, a warp-uniform register choice instead of a select chain per register.)
         if (has_phantom) phantom_patch16(d, U1{});                       // inputs of the first tail step
         while (d < d_end && !fired && !redo && !band_exit) {
             if (d - d_check >= 32) { if (!check_range(d, S1{})) { redo = true; break; } d_check = d; }
