@@ -180,7 +180,7 @@ typedef struct {
     int32_t n_devices;        /* <= 0: use all visible devices */
     const int32_t *devices;   /* optional list of ordinals, NULL = 0..n_devices-1 */
     uint32_t batch_alns;      /* alignments per batch, 0 = default (8192) */
-    int32_t streams_per_device; /* 0 = default (3) */
+    int32_t streams_per_device; /* 0 = default (5): batches in flight per device; below 4 the device runs short of launched kernels */
     int32_t staging_threads;  /* host threads per device that copy sequences into pinned staging, 0 = min(8, cores / devices) */
     const uint8_t *query_ops; /* optional per-pair op bytes (bit 0 reverse, bit 1 complement); both NULL = no ops */
     const uint8_t *target_ops;
