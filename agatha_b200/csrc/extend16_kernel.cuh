@@ -36,7 +36,7 @@
 #include "extend_kernel.cuh"
 
 #ifndef AGATHA_MB24
-#define AGATHA_MB24 3
+#define AGATHA_MB24 4            // CTAs per SM of the one-warp shapes with C <= 24 (measured on C2: 2 -> 63.4 ms, 3 -> 58.8, 4 -> 57.1)
 #endif
 #ifndef AGATHA_MBW4
 #define AGATHA_MBW4 3
@@ -59,7 +59,8 @@ struct Shape16 {
     static constexpr int groups = NW == 1 ? 4 : 1;                 // alignments in flight per CTA
     static constexpr int warps = NW * groups;
     static constexpr int threads = 32 * warps;
-    // register budget: C = 8/16/24 fit 128 registers (4 CTAs of 4 warps per SM), C = 32 gets 168 (3 CTAs)
+    // register budget: C = 8/16/24 run with 128 registers (4 CTAs of 4 warps per SM; C = 24 spills six registers outside its
+    // steady-state loop, which costs less than the fourth CTA brings), C = 32 gets 168 (3 CTAs; at 128 it spills in the loop)
     static constexpr int min_blocks = NW == 1 ? (C <= 24 ? AGATHA_MB24 : 3) : (NW == 2 ? 6 : (NW == 4 ? AGATHA_MBW4 : 1));
 };
 
@@ -70,6 +71,7 @@ struct Shape16 {
 __device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) { emu::mbar_init(b, count); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) { emu::mbar_arrive(b); }
 __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) { emu::mbar_wait(b, parity); }
+__device__ __forceinline__ bool mbar_test(uint64_t* b, unsigned parity) { return emu::mbar_test(b, parity); }
 #else
 __device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count)
 {
@@ -90,6 +92,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity)  // acqu
         "bra AGATHA_MBAR_WAIT;\n"
         "AGATHA_MBAR_DONE:\n"
         "}" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* b, unsigned parity)  // the same question without waiting (acquire when true)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}" : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+    return ok != 0u;
 }
 #endif
 
@@ -260,7 +273,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         // ptxas keeps warp-uniform values in uniform registers and copies them into a vector register in front of every PRMT
         // (the table operand cannot be uniform): 12 moves per two anti-diagonals. A value that went through a shuffle is not
         // uniform in its eyes, so the table stays in two ordinary registers for the whole alignment.
-        const unsigned z = __shfl_sync(FULL, 0u, lane);
+        const unsigned z = (NW > 1) ? (unsigned)(lane >= p.k32) : __shfl_sync(FULL, 0u, lane);   // 0; k32 = 32 is opaque to ptxas
         k.tab_lo ^= z; k.tab_hi ^= z;
     }
     unsigned A0[P], A1[P], AE[P], AF[P];
@@ -677,10 +690,12 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     //     computed after the one that stops the alignment.
     // The pipeline is entered behind a __syncthreads (pipe_enter) and left through pipe_drain, which tests what is pending.
     int pipe_lo = 0;                                                     // first anti-diagonal computed by the current pipeline run
+    bool pipe_ready = false;                                             // the phase the next wait is about is already known to be complete
     int ev_d = 0;                                                        // anti-diagonal saved in evsnap
     auto pipe_enter = [&](int d0) {
         if (lane == 0) mbar_arrive(&sm->mbar[(d0 - 1) & 1]);             // phase "d0-1": those edge values are published (lock step)
         pipe_lo = d0;
+        pipe_ready = false;
     };
     // test of anti-diagonal dt given the per-warp maxima `v` (lane w < NW: warp w's; INT_MIN elsewhere); A: its H values.
     // True = it might fire Z-drop (cold path).
@@ -711,7 +726,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             unsigned x = __shfl_up_sync(FULL, AE[P - 1], 1);
             const unsigned out = out_edge16<C, 0>(A0, AE, AF, Qw, Rw, k);
             if (lane == 0) { sm->edgeF[ws][warp] = out; mbar_arrive(&sm->mbar[1]); }      // odd anti-diagonal
-            mbar_wait(&sm->mbar[0], mphase & 1u);
+            if (!pipe_ready) mbar_wait(&sm->mbar[0], mphase & 1u);
             mphase ^= 1u;
             const int v = load_maxima(dd - 2);
             if (lane == 0) x = (warp == 0) ? (FLOORU16 << 16) : sm->edgeE[rs][warp > 0 ? warp - 1 : 0];
@@ -719,13 +734,16 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             if (slow) { snapshot_ev(A0); ev_d = dd - 2; }
             const unsigned ein = prmt(x, AE[P - 1], 0x5432);
             best2 = cells16<C, 0, false>(A0, AE, AF, Qw, Rw, ein, k, 0u);
+            // has everybody arrived for THIS anti-diagonal already? (asked here, answered by the time the next step wants to know:
+            // the barrier unit takes some fifty cycles to answer, which the step after the next wait would otherwise sit out)
+            pipe_ready = mbar_test(&sm->mbar[1], (mphase >> 1) & 1u);
             AE[JP] = prmt(AE[JP], floor2, edge_sel);
             shift_ref_blk();
         } else {
             unsigned y = __shfl_down_sync(FULL, AF[0], 1);
             const unsigned out = out_edge16<C, 1>(A1, AE, AF, Qw, Rw, k);
             if (lane == 31) { sm->edgeE[ws][warp] = out; mbar_arrive(&sm->mbar[0]); }     // even anti-diagonal
-            mbar_wait(&sm->mbar[1], (mphase >> 1) & 1u);
+            if (!pipe_ready) mbar_wait(&sm->mbar[1], (mphase >> 1) & 1u);
             mphase ^= 2u;
             const int v = load_maxima(dd - 2);
             if (lane == 31) y = (warp == NW - 1) ? FLOORU16 : sm->edgeF[rs][warp < NW - 1 ? warp + 1 : 0];
@@ -733,6 +751,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             if (slow) { snapshot_ev(A1); ev_d = dd - 2; }
             const unsigned fin = prmt(AF[0], y, 0x5432);
             best2 = cells16<C, 1, false>(A1, AE, AF, Qw, Rw, fin, k, 0u);
+            pipe_ready = mbar_test(&sm->mbar[0], mphase & 1u);
             AF[JP] = prmt(AF[JP], floor2, edge_sel);
             shift_query_blk();
         }
@@ -752,8 +771,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
             // phase dn-1, the one arrival nobody has waited for yet (every phase is waited for exactly once, whatever happens
             // below): everybody has finished step dn-2
             const int b = (dn - 1) & 1;
-            mbar_wait(&sm->mbar[b], (mphase >> b) & 1u);
+            if (!pipe_ready) mbar_wait(&sm->mbar[b], (mphase >> b) & 1u);
             mphase ^= 1u << b;
+            pipe_ready = false;
         }
 #pragma unroll 1
         for (int i = slow ? 0 : 1; i < 3; i++) {

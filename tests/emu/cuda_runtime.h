@@ -118,6 +118,8 @@ inline void mbar_wait(uint64_t* b, unsigned parity)
     }
 }
 
+inline bool mbar_test(uint64_t* b, unsigned parity) { return (unsigned)((*(volatile uint64_t*)b >> 32) & 1u) != (parity & 1u); }
+
 }  // namespace emu
 
 #define threadIdx (emu::cur->tid)
