@@ -27,8 +27,11 @@
 //     P registers; its position is searched only when a Z-drop test or the end of the alignment needs it;
 //   * the steady state runs in blocks of 16 anti-diagonals: the sequence feeds of a block are loaded once at its top (one
 //     coalesced word per lane and sequence), the inner two-anti-diagonal body carries no load, no bounds test;
-//   * multi-warp groups (W > 1023): lane-edge hand-over and per-warp maxima through shared memory, one barrier per
-//     anti-diagonal; range monitor, re-basing and events are decided group-wide so that all warps stay in lock step;
+//   * multi-warp groups (W > 1023): lane-edge hand-over and per-warp maxima through shared memory. Prologue and tail run in
+//     lock step (one barrier per anti-diagonal; warps without a cell inside the matrix skip the cell update); the steady
+//     state is pipelined over two arrive / wait barriers -- a warp publishes its edge value before it waits for its
+//     neighbours', maxima are tested two anti-diagonals late, the range monitor runs inside the pipeline (see "pipelined
+//     steady state" below). Re-basing and events are decided group-wide;
 //   * the tail runs packed to the very end, including the anti-diagonals without any cell and the wrap-up scan
 //     (agatha_kernel.h:334-356).
 #pragma once
