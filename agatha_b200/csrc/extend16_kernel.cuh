@@ -372,15 +372,15 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     int mx_h = bias + D(0), mx_d = 0;                                    // true 0 (agatha_kernel.h:158)
     int thrS = mx_h - Zeff - dod;                                        // step 0 adds delta(-1) = dod first
     auto sync_state = [&]() { st.max = mx_h - bias + base - D(mx_d); st.thr = scan_threshold(st.max, p); };   // cold: before scan_update / output
-    // Range monitor (every 32 anti-diagonals). Stored H never decreases along a diagonal, so the low end only moves when the
+    // Range monitor (every RANGE16_PERIOD = 64 anti-diagonals; RANGE16_PAIRS = 33). Stored H never decreases along a diagonal, so the low end only moves when the
     // state is re-based; low_ok keeps t = M - goe + delta free of borrows and the floor below every live candidate. At the top
     // a live value rises by at most (match + X) per two anti-diagonals. neg_ok: the lowest TRUE live value for which
-    // MINUS_INF2 (-16384) outside the band still loses every maximum it enters during the next 34 anti-diagonals.
+    // MINUS_INF2 (-16384) outside the band still loses every maximum it enters during the next 2 * RANGE16_PAIRS anti-diagonals.
     // Dead (out-of-band) cells creep upwards from the floor by at most (match + X) per two anti-diagonals between two checks
-    // (they are pushed back at every check) and must stay below every live value: hence the 17 * (match + X).
-    const int low_ok = (int)FLOORU16 + 17 * (max(p.match, 0) + X) + p.goe + 2 * p.ge + 64;
-    const int high_ok = 65535 - 17 * (max(p.match, 0) + X) - 64;
-    const int neg_ok = NEG16 + p.goe + p.ge + 17 * X + 64;
+    // (they are pushed back at every check) and must stay below every live value: hence the RANGE16_PAIRS * (match + X).
+    const int low_ok = (int)FLOORU16 + RANGE16_PAIRS * (max(p.match, 0) + X) + p.goe + 2 * p.ge + 64;
+    const int high_ok = 65535 - RANGE16_PAIRS * (max(p.match, 0) + X) - 64;
+    const int neg_ok = NEG16 + p.goe + p.ge + RANGE16_PAIRS * X + 64;
 
     // ---- snapshot of the anti-diagonal that holds the running maximum (shared memory) ------------------------------------
     int snap_d = -1, snap_u = 0, snap_w = 0, snap_h = 0;
@@ -888,17 +888,17 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     };
     if constexpr (NW > 1) {
         // ---- steady state of a multi-warp group: pipelined blocks of 16 anti-diagonals ------------------------------------------
-        // The range monitor does not interrupt the pipeline: every second block each warp pushes its dead positions back, takes
+        // The range monitor does not interrupt the pipeline: every fourth block each warp pushes its dead positions back, takes
         // the minimum / maximum of its own live values and publishes them; two anti-diagonals later (everybody has published by
-        // then, and 32 + 2 anti-diagonals is what the margins of low_ok / high_ok cover) the group-wide values are looked at. Only
+        // then, and 64 + 2 anti-diagonals is what the margins of low_ok / high_ok cover) the group-wide values are looked at. Only
         // when they call for a re-basing or a hand-over does the group leave the pipeline for the full check (check_range).
         while (!fired && d + 16 <= d_fast_hi) {
-            if (d - d_check >= 32) { if (!check_range(d, S1{})) { redo = true; break; } d_check = d; }
+            if (d - d_check >= RANGE16_PERIOD) { if (!check_range(d, S1{})) { redo = true; break; } d_check = d; }
             pipe_enter(d);                                               // (everybody is behind a barrier here)
             int ev = 0;
             bool rng_pending = false;
             for (;;) {
-                if (AGATHA_ASYNC_RANGE && d - d_check >= 32) {
+                if (AGATHA_ASYNC_RANGE && d - d_check >= RANGE16_PERIOD) {
                     int mn, mx;
                     range_local(mn, mx, S1{});
                     if (lane == 31) { sm->rng[0][warp] = mn; sm->rng[1][warp] = mx; }   // lane 31 arrives next (even anti-diagonal)
@@ -919,7 +919,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
                     }
                 }
                 if (ev || d + 16 > d_fast_hi) break;
-                if (!AGATHA_ASYNC_RANGE && d - d_check >= 32) break;
+                if (!AGATHA_ASYNC_RANGE && d - d_check >= RANGE16_PERIOD) break;
             }
             // cold: out of the pipeline. ev == 1: steps up to d are computed, ev == 2: up to d + 1, otherwise up to d - 1.
             if (pipe_drain(d + (ev < 3 ? ev : 0), ev == 1 || ev == 2)) break;
@@ -928,13 +928,13 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
                 if (step16(d + 1, true, U0{}, MSTEADY{}, INBLK{}, inject_pro)) { if (scan_slow(A0, d + 1, 0, 0)) { fired = true; d++; break; } }
             }
             if (ev == 1 || ev == 2) d += 2;
-            if (ev == 3 || rng_pending) d_check = d - 32;                // the full check, now
+            if (ev == 3 || rng_pending) d_check = d - RANGE16_PERIOD;                // the full check, now
         }
         if (!fired && !redo) { window_pos(d); refeed(); }
     } else if (!fired) {
-        // ---- steady state: blocks of 16 anti-diagonals, range check every second block --------------------------------------
+        // ---- steady state: blocks of 16 anti-diagonals, range check every fourth block --------------------------------------
         while (d + 16 <= d_fast_hi && !fired && !redo) {
-            if (d - d_check >= 32) { if (!check_range(d, S0{})) { redo = true; break; } d_check = d; }
+            if (d - d_check >= RANGE16_PERIOD) { if (!check_range(d, S0{})) { redo = true; break; } d_check = d; }
             block_feeds();
             const int dblk = d + 16;
 #if AGATHA_INLINE_EVENTS
@@ -983,8 +983,8 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         // did help is the patch's cheaper poke, a warp-uniform register choice instead of a select chain per register.)
         if (has_phantom) phantom_patch16(d, U1{});                       // inputs of the first tail step
         while (d < d_end && !fired && !redo && !band_exit) {
-            if (d - d_check >= 32) { if (!check_range(d, S1{})) { redo = true; break; } d_check = d; }
-            const int dchunk = min(d_end, d_check + 32);
+            if (d - d_check >= RANGE16_PERIOD) { if (!check_range(d, S1{})) { redo = true; break; } d_check = d; }
+            const int dchunk = min(d_end, d_check + RANGE16_PERIOD);
             int ev = 0;
 #pragma unroll 1
             for (; d < dchunk; d += 2) {

@@ -93,8 +93,8 @@ inline int make_kernel_params(const agatha_params_t* p, KernelParams* kp)
         const long long X = p->mismatch, half = (p->band_width + 2) / 2;
         const long long creep = (p->match + X) * half;
         const long long lowtrue = 3LL * kp->goe + (long long)kp->ge * (p->band_width + 2) + X * half + 128;
-        const long long bias = 4000 /* FLOORU16 */ + creep + lowtrue + kp->goe + 2LL * kp->ge + 17 * (p->match + X) + 320;
-        const bool fits = bias + creep + 2048 < 65535 - 17 * (p->match + X);
+        const long long bias = 4000 /* FLOORU16 */ + creep + lowtrue + kp->goe + 2LL * kp->ge + RANGE16_PAIRS * (p->match + X) + 320;
+        const bool fits = bias + creep + 2048 < 65535 - RANGE16_PAIRS * (p->match + X);
         // (MINUS_INF2 is not read during the prologue -- the band edges are still outside the matrix -- and the range check
         // that follows it tests the lowest live value against the sentinel before the steady state uses it)
         if (fits) {

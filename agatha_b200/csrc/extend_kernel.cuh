@@ -35,6 +35,11 @@
 namespace agatha {
 
 constexpr int NEG16 = -16384;        // the reference's MINUS_INF2 (gasal_kernels.h:39); exact value matters for parity
+// Packed kernel (extend16_kernel.cuh): its range monitor looks at the live values every RANGE16_PERIOD anti-diagonals and its
+// margins cover RANGE16_PAIRS pairs of anti-diagonals (the period plus two: a multi-warp group evaluates the check two steps
+// late). Round 2 ran it every 32: a source-level profile of the 1-8 kb workload put 8 % of the kernel's time there.
+constexpr int RANGE16_PERIOD = 64;
+constexpr int RANGE16_PAIRS = RANGE16_PERIOD / 2 + 1;
 constexpr int NEGBIG = -(1 << 25);   // "never a real score"; NEGBIG*32 still fits int32 (tracking keys)
 constexpr unsigned FULL = 0xffffffffu;
 
