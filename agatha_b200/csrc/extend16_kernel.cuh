@@ -372,7 +372,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     int mx_h = bias + D(0), mx_d = 0;                                    // true 0 (agatha_kernel.h:158)
     int thrS = mx_h - Zeff - dod;                                        // step 0 adds delta(-1) = dod first
     auto sync_state = [&]() { st.max = mx_h - bias + base - D(mx_d); st.thr = scan_threshold(st.max, p); };   // cold: before scan_update / output
-    // Range monitor (every RANGE16_PERIOD = 64 anti-diagonals; RANGE16_PAIRS = 33). Stored H never decreases along a diagonal, so the low end only moves when the
+    // Range monitor (every RANGE16_PERIOD = 256 anti-diagonals; RANGE16_PAIRS = 129). Stored H never decreases along a diagonal, so the low end only moves when the
     // state is re-based; low_ok keeps t = M - goe + delta free of borrows and the floor below every live candidate. At the top
     // a live value rises by at most (match + X) per two anti-diagonals. neg_ok: the lowest TRUE live value for which
     // MINUS_INF2 (-16384) outside the band still loses every maximum it enters during the next 2 * RANGE16_PAIRS anti-diagonals.
@@ -888,9 +888,9 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     };
     if constexpr (NW > 1) {
         // ---- steady state of a multi-warp group: pipelined blocks of 16 anti-diagonals ------------------------------------------
-        // The range monitor does not interrupt the pipeline: every fourth block each warp pushes its dead positions back, takes
+        // The range monitor does not interrupt the pipeline: every RANGE16_PERIOD anti-diagonals each warp pushes its dead positions back, takes
         // the minimum / maximum of its own live values and publishes them; two anti-diagonals later (everybody has published by
-        // then, and 64 + 2 anti-diagonals is what the margins of low_ok / high_ok cover) the group-wide values are looked at. Only
+        // then, and the period + 2 anti-diagonals is what the margins of low_ok / high_ok cover) the group-wide values are looked at. Only
         // when they call for a re-basing or a hand-over does the group leave the pipeline for the full check (check_range).
         while (!fired && d + 16 <= d_fast_hi) {
             if (d - d_check >= RANGE16_PERIOD) { if (!check_range(d, S1{})) { redo = true; break; } d_check = d; }
@@ -932,7 +932,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
         }
         if (!fired && !redo) { window_pos(d); refeed(); }
     } else if (!fired) {
-        // ---- steady state: blocks of 16 anti-diagonals, range check every fourth block --------------------------------------
+        // ---- steady state: blocks of 16 anti-diagonals, range check every RANGE16_PERIOD --------------------------------------
         while (d + 16 <= d_fast_hi && !fired && !redo) {
             if (d - d_check >= RANGE16_PERIOD) { if (!check_range(d, S0{})) { redo = true; break; } d_check = d; }
             block_feeds();

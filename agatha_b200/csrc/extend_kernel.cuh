@@ -37,8 +37,14 @@ namespace agatha {
 constexpr int NEG16 = -16384;        // the reference's MINUS_INF2 (gasal_kernels.h:39); exact value matters for parity
 // Packed kernel (extend16_kernel.cuh): its range monitor looks at the live values every RANGE16_PERIOD anti-diagonals and its
 // margins cover RANGE16_PAIRS pairs of anti-diagonals (the period plus two: a multi-warp group evaluates the check two steps
-// late). Round 2 ran it every 32: a source-level profile of the 1-8 kb workload put 8 % of the kernel's time there.
-constexpr int RANGE16_PERIOD = 64;
+// late). It used to run every 32: a source-level profile of the 1-8 kb workload put 8 % of the kernel's time there (the check
+// is cold code, every visit costs instruction fetch on top of its 250 instructions). Measured, C1 / C2 / C4 GCUPS on one box:
+// 64 -> 2,914 / 4,322 / 2,741; 128 -> 3,083 / 4,392 / 2,932; 256 -> 3,186 / 4,489 / 2,942. The price is the margin: parameter
+// sets whose scores are so large that 129 * (match + mismatch) no longer fits the window go to the general kernel.
+#ifndef AGATHA_RANGE16_PERIOD
+#define AGATHA_RANGE16_PERIOD 256
+#endif
+constexpr int RANGE16_PERIOD = AGATHA_RANGE16_PERIOD;
 constexpr int RANGE16_PAIRS = RANGE16_PERIOD / 2 + 1;
 constexpr int NEGBIG = -(1 << 25);   // "never a real score"; NEGBIG*32 still fits int32 (tracking keys)
 constexpr unsigned FULL = 0xffffffffu;
