@@ -341,6 +341,9 @@ def roofline_for(ag, leg, res, kernel_ms, W, int_peak, qlen, tlen, ncu_name=None
     else:
         r.update({"peak": None, "frac": None, "note": "hot-loop statistics unavailable (no cuobjdump and no committed profile)"})
     ncu = load_ncu(ncu_name) if ncu_name else None
+    # traffic is per launch like `achieved`: only a capture of a launch over the same number of pairs qualifies
+    if ncu and ncu.get("pairs") not in (None, len(qlen)):
+        ncu = None
     r["traffic"] = ncu.get("dram_bytes_per_launch") if ncu else None
     if ncu:
         r["ncu"] = {k: ncu.get(k) for k in ("alu_pipe_pct", "fma_pipe_pct", "issue_active_pct", "warps_active_pct", "source", "pairs")}
