@@ -47,7 +47,7 @@ def test_random_pairs_vs_oracle(oracle, W, sw, Z, m, go):
 
 @pytest.mark.parametrize("W,hi", [(1031, 3000), (2047, 5000), (2055, 5000), (4095, 7000), (4103, 9000), (8191, 9000)])
 def test_wide_bands_multi_warp_groups(oracle, W, hi):
-    # bands wider than one warp's registers: NW = 2, 4, 8 warps per alignment, one barrier per anti-diagonal
+    # bands wider than one warp's registers: NW = 2, 4, 8 warps per alignment (pipelined steady state over arrive / wait barriers)
     pairs = make_pairs(9700 + W, 40, 1, hi, mixed=True) + make_pairs(9800 + W, 6, hi, hi + 500, err=0.01)
     _cmp_oracle(oracle, pairs, dict(band_width=W), "wide")
     _cmp_oracle(oracle, pairs[:24], dict(band_width=W, z_threshold=60, slice_width=1), "wide z60")
