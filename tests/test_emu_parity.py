@@ -49,6 +49,13 @@ def test_emulated_wide_bands_multi_warp_groups(emu, oracle, W, hi):
     assert emu.last_used_packed() == (W % 8 == 7)            # the packed kernel covers W = 7 (mod 8); the general kernel the rest
     _cmp(emu, oracle, pairs, dict(band_width=W), "wide, general kernel only", s16=2)
     assert not emu.last_used_packed()
+    # the long clean pairs (target lengths not multiples of 8: padding-column patches in the tail, warps that skip part of the
+    # prologue) must be finished by the packed kernel itself: the range monitor once mistook the stored floor of a patched
+    # input for a live value on its way down and handed such pairs to the general kernel -- same results, ten times the cost
+    long_pairs = [pr for pr in make_pairs(9800 + W, 2, hi, hi + 300, err=0.01)]
+    long_pairs = [(q, t[:len(t) - (len(t) % 8 == 0)]) for q, t in long_pairs]
+    _cmp(emu, oracle, long_pairs, dict(band_width=W), "wide, long pairs")
+    assert emu.last_used_packed() and emu.last_redo_count() == 0
 
 
 def test_emulated_edge_cases_and_rare_symbols(emu, oracle):
