@@ -372,7 +372,7 @@ __device__ __forceinline__ bool run_pair16(const Pair& pr, const KernelParams& p
     int mx_h = bias + D(0), mx_d = 0;                                    // true 0 (agatha_kernel.h:158)
     int thrS = mx_h - Zeff - dod;                                        // step 0 adds delta(-1) = dod first
     auto sync_state = [&]() { st.max = mx_h - bias + base - D(mx_d); st.thr = scan_threshold(st.max, p); };   // cold: before scan_update / output
-    // Range monitor (every RANGE16_PERIOD = 256 anti-diagonals; RANGE16_PAIRS = 129). Stored H never decreases along a diagonal, so the low end only moves when the
+    // Range monitor (every RANGE16_PERIOD = 512 anti-diagonals; RANGE16_PAIRS = 257). Stored H never decreases along a diagonal, so the low end only moves when the
     // state is re-based; low_ok keeps t = M - goe + delta free of borrows and the floor below every live candidate. At the top
     // a live value rises by at most (match + X) per two anti-diagonals. neg_ok: the lowest TRUE live value for which
     // MINUS_INF2 (-16384) outside the band still loses every maximum it enters during the next 2 * RANGE16_PAIRS anti-diagonals.

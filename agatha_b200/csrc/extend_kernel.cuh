@@ -39,10 +39,11 @@ constexpr int NEG16 = -16384;        // the reference's MINUS_INF2 (gasal_kernel
 // margins cover RANGE16_PAIRS pairs of anti-diagonals (the period plus two: a multi-warp group evaluates the check two steps
 // late). It used to run every 32: a source-level profile of the 1-8 kb workload put 8 % of the kernel's time there (the check
 // is cold code, every visit costs instruction fetch on top of its 250 instructions). Measured, C1 / C2 / C4 GCUPS on one box:
-// 64 -> 2,914 / 4,322 / 2,741; 128 -> 3,083 / 4,392 / 2,932; 256 -> 3,186 / 4,489 / 2,942. The price is the margin: parameter
-// sets whose scores are so large that 129 * (match + mismatch) no longer fits the window go to the general kernel.
+// 64 -> 2,914 / 4,322 / 2,741; 128 -> 3,083 / 4,392 / 2,932; 256 -> 3,186 / 4,489 / 2,942; on another box 256 -> 3,220 / 4,509 /
+// 2,966; 512 -> 3,336 / 4,538 / 2,974; 1024 -> 3,366 / 4,549 / 3,121. The price is the margin: parameter sets whose scores
+// are so large that 257 * (match + mismatch) no longer fits the window go to the general kernel; 512 it is.
 #ifndef AGATHA_RANGE16_PERIOD
-#define AGATHA_RANGE16_PERIOD 256
+#define AGATHA_RANGE16_PERIOD 512
 #endif
 constexpr int RANGE16_PERIOD = AGATHA_RANGE16_PERIOD;
 constexpr int RANGE16_PAIRS = RANGE16_PERIOD / 2 + 1;
