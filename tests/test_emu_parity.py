@@ -58,6 +58,18 @@ def test_emulated_wide_bands_multi_warp_groups(emu, oracle, W, hi):
     assert emu.last_used_packed() and emu.last_redo_count() == 0
 
 
+@pytest.mark.parametrize("sched", [1, 2, 5])
+def test_emulated_pipelined_groups_under_other_fibre_schedules(emu, oracle, sched, monkeypatch):
+    """The pipelined steady state of multi-warp groups (arrive / wait barriers, double-buffered hand-over slots, maxima tested
+    two anti-diagonals late) must not depend on the order in which warps get their turn: backward order (1) and reshuffled
+    orders with warps held back for dozens of rounds (2, 5). The warp boundary of W = 2047 lies on the main diagonal, so a
+    wrong hand-over value changes scores."""
+    monkeypatch.setenv("AGATHA_EMU_SCHED", str(sched))
+    pairs = make_pairs(9900 + sched, 3, 2100, 3200, mixed=True) + make_pairs(9950 + sched, 1, 4200, 4400, err=0.02)
+    _cmp(emu, oracle, pairs, dict(band_width=2047, z_threshold=200), "wide, schedule %d" % sched)
+    assert emu.last_used_packed()
+
+
 def test_emulated_edge_cases_and_rare_symbols(emu, oracle):
     pairs = [("", "ACGT"), ("ACGT", ""), ("A", "A"), ("T", "A"), ("NNNN", "NNNN"), ("ACGTACGTA", "ACG"), ("ACG", "ACGTACGTACGT"),
              ("acgtacgt", "ACGTACGT"), ("ACGTNACGT", "ACGTNACGT"), ("A" * 40, "A" * 40), ("ACGT" * 10, "TGCA" * 10)]
